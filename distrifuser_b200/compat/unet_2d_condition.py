@@ -1,0 +1,330 @@
+"""UNet2DConditionModel for environments without `diffusers` (this image has none and no network).
+
+The reference pins diffusers==0.24.0 (setup.py:14) and wraps its UNet2DConditionModel
+(distrifuser/models/distri_sdxl_unet_pp.py:16-40).  This module provides the same module tree -- attribute names,
+call signatures and state-dict keys of the SD1.x / SDXL configurations -- so that DistriUNetPP's surgery and
+real checkpoints work unchanged, and `DistriSDXLPipeline.from_pretrained` uses the real diffusers class when it
+is importable.  Activations are kept NHWC (torch.channels_last) end to end: the [b,C,h,w] <-> [b,hw,C] reshapes
+around the transformer blocks are then free views and cuDNN gets tensor-core friendly layouts.
+"""
+from __future__ import annotations
+
+import math
+from types import SimpleNamespace
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+SDXL = dict(
+    in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280), layers_per_block=2,
+    down_block_types=("DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"),
+    up_block_types=("CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"),
+    transformer_layers_per_block=(1, 2, 10), attention_head_dim=(5, 10, 20), cross_attention_dim=2048,
+    use_linear_projection=True, norm_num_groups=32, norm_eps=1e-5, addition_embed_type="text_time",
+    addition_time_embed_dim=256, projection_class_embeddings_input_dim=2816, sample_size=128,
+)
+SD15 = dict(
+    in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+    down_block_types=("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",),
+    up_block_types=("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3,
+    transformer_layers_per_block=(1, 1, 1, 1), attention_head_dim=(8, 8, 8, 8), cross_attention_dim=768,
+    use_linear_projection=False, norm_num_groups=32, norm_eps=1e-5, addition_embed_type=None,
+    addition_time_embed_dim=None, projection_class_embeddings_input_dim=None, sample_size=64,
+)
+
+
+class UNet2DConditionOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class Attention(nn.Module):
+    """Attribute contract read by DistriAttentionPP (attn.py:16-38,93-100)."""
+
+    def __init__(self, query_dim, cross_attention_dim, heads, dim_head):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.inner_dim = heads, inner
+        self.residual_connection, self.rescale_output_factor = False, 1.0
+        kv_dim = query_dim if cross_attention_dim is None else cross_attention_dim
+        self.to_q = nn.Linear(query_dim, inner, bias=False)
+        self.to_k = nn.Linear(kv_dim, inner, bias=False)
+        self.to_v = nn.Linear(kv_dim, inner, bias=False)
+        self.to_out = nn.ModuleList([nn.Linear(inner, query_dim), nn.Dropout(0.0)])
+
+    def forward(self, hidden_states, encoder_hidden_states=None, **kw):
+        raise RuntimeError("Attention must be wrapped by DistriSelfAttentionPP / DistriCrossAttentionPP "
+                           "(distrifuser_b200 has no unfused attention path)")
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, 4 * dim), nn.Dropout(0.0), nn.Linear(4 * dim, dim)])
+
+    def forward(self, x):
+        return self.net[2](self.net[0](x))
+
+
+class BasicTransformerBlock(nn.Module):
+    def __init__(self, dim, heads, head_dim, cross_dim):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn1 = Attention(dim, None, heads, head_dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.attn2 = Attention(dim, cross_dim, heads, head_dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, encoder_hidden_states=None):
+        x = x + self.attn1(self.norm1(x), encoder_hidden_states=None)
+        x = x + self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states)
+        return x + self.ff(self.norm3(x))
+
+
+class Transformer2DModel(nn.Module):
+    def __init__(self, heads, head_dim, channels, depth, cross_dim, groups, linear_proj):
+        super().__init__()
+        inner = heads * head_dim
+        self.use_linear_projection = linear_proj
+        self.norm = nn.GroupNorm(groups, channels, eps=1e-6)
+        self.proj_in = nn.Linear(channels, inner) if linear_proj else nn.Conv2d(channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(inner, heads, head_dim, cross_dim) for _ in range(depth)])
+        self.proj_out = nn.Linear(inner, channels) if linear_proj else nn.Conv2d(inner, channels, 1)
+
+    @staticmethod
+    def _tokens(x):  # [b,C,h,w] (NHWC memory) -> [b,hw,C] without a copy
+        b, c, h, w = x.shape
+        return x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+
+    @staticmethod
+    def _image(t, h, w):  # [b,hw,C] -> [b,C,h,w] NHWC memory, no copy
+        b, _, c = t.shape
+        return t.reshape(b, h, w, c).permute(0, 3, 1, 2)
+
+    def forward(self, x, encoder_hidden_states=None):
+        _, _, h, w = x.shape
+        res = x
+        x = self.norm(x)
+        if self.use_linear_projection:
+            t = self.proj_in(self._tokens(x))
+        else:
+            t = self._tokens(self.proj_in(x))
+        for blk in self.transformer_blocks:
+            t = blk(t, encoder_hidden_states=encoder_hidden_states)
+        if self.use_linear_projection:
+            x = self._image(self.proj_out(t), h, w)
+        else:
+            x = self.proj_out(self._image(t, h, w))
+        return x + res
+
+
+class ResnetBlock2D(nn.Module):
+    def __init__(self, cin, cout, temb, groups, eps):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, cin, eps=eps)
+        self.conv1 = nn.Conv2d(cin, cout, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb, cout)
+        self.norm2 = nn.GroupNorm(groups, cout, eps=eps)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
+        self.nonlinearity = nn.SiLU()
+        self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
+        self.output_scale_factor = 1.0
+        self.fused_norm_act = False      # DistriUNetPP turns this on: SiLU runs inside the GroupNorm kernel
+
+    def forward(self, x, temb):
+        h = self.norm1(x)
+        if not self.fused_norm_act:
+            h = self.nonlinearity(h)
+        h = self.conv1(h)
+        h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
+        h = self.norm2(h)
+        if not self.fused_norm_act:
+            h = self.nonlinearity(h)
+        h = self.conv2(h)
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        return x + h
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, stride=2, padding=1)
+
+    def forward(self, x):
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class _Down(nn.Module):
+    def __init__(self, cin, cout, temb, layers, groups, eps, downsample, attn):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb, groups, eps) for i in range(layers)])
+        if attn is not None:
+            self.attentions = nn.ModuleList([Transformer2DModel(channels=cout, groups=groups, **attn) for _ in range(layers)])
+        self.has_cross_attention = attn is not None
+        self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if downsample else None
+
+    def forward(self, x, temb, ehs):
+        skips = []
+        for i, res in enumerate(self.resnets):
+            x = res(x, temb)
+            if self.has_cross_attention:
+                x = self.attentions[i](x, encoder_hidden_states=ehs)
+            skips.append(x)
+        if self.downsamplers is not None:
+            x = self.downsamplers[0](x)
+            skips.append(x)
+        return x, skips
+
+
+class _Mid(nn.Module):
+    def __init__(self, c, temb, groups, eps, attn):
+        super().__init__()
+        self.resnets = nn.ModuleList([ResnetBlock2D(c, c, temb, groups, eps) for _ in range(2)])
+        self.attentions = nn.ModuleList([Transformer2DModel(channels=c, groups=groups, **attn)])
+
+    def forward(self, x, temb, ehs):
+        x = self.resnets[0](x, temb)
+        x = self.attentions[0](x, encoder_hidden_states=ehs)
+        return self.resnets[1](x, temb)
+
+
+class _Up(nn.Module):
+    def __init__(self, cin, cout, prev, temb, layers, groups, eps, upsample, attn):
+        super().__init__()
+        self.resnets = nn.ModuleList()
+        for i in range(layers):
+            skip = cin if i == layers - 1 else cout
+            self.resnets.append(ResnetBlock2D((prev if i == 0 else cout) + skip, cout, temb, groups, eps))
+        if attn is not None:
+            self.attentions = nn.ModuleList([Transformer2DModel(channels=cout, groups=groups, **attn) for _ in range(layers)])
+        self.has_cross_attention = attn is not None
+        self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if upsample else None
+
+    def forward(self, x, skips, temb, ehs):
+        for i, res in enumerate(self.resnets):
+            x = res(torch.cat([x, skips.pop()], dim=1), temb)
+            if self.has_cross_attention:
+                x = self.attentions[i](x, encoder_hidden_states=ehs)
+        if self.upsamplers is not None:
+            x = self.upsamplers[0](x)
+        return x
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        return self.linear_2(self.act(self.linear_1(x)))
+
+
+def sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
+    """diffusers Timesteps(dim, flip_sin_to_cos=True, downscale_freq_shift=0): [cos | sin]."""
+    half = dim // 2
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    ang = t[:, None].float() * freqs[None]
+    return torch.cat([torch.cos(ang), torch.sin(ang)], dim=-1)
+
+
+class UNet2DConditionModel(nn.Module):
+    def __init__(self, **overrides):
+        super().__init__()
+        cfg = dict(SDXL)
+        cfg.update(overrides)
+        self.config = SimpleNamespace(**cfg)
+        c = self.config
+        boc, g, eps = tuple(c.block_out_channels), c.norm_num_groups, c.norm_eps
+        temb = boc[0] * 4
+        heads, depth = tuple(c.attention_head_dim), tuple(c.transformer_layers_per_block)
+        nb = len(boc)
+
+        def attn_cfg(i, ch):
+            return dict(heads=heads[i], head_dim=ch // heads[i], depth=depth[i], cross_dim=c.cross_attention_dim,
+                        linear_proj=c.use_linear_projection)
+
+        self.conv_in = nn.Conv2d(c.in_channels, boc[0], 3, padding=1)
+        self.time_embedding = TimestepEmbedding(boc[0], temb)
+        if c.addition_embed_type == "text_time":
+            self.add_embedding = TimestepEmbedding(c.projection_class_embeddings_input_dim, temb)
+        self.down_blocks = nn.ModuleList()
+        ch = boc[0]
+        for i, kind in enumerate(c.down_block_types):
+            cin, ch = ch, boc[i]
+            self.down_blocks.append(_Down(cin, ch, temb, c.layers_per_block, g, eps, i != nb - 1,
+                                          attn_cfg(i, ch) if kind.startswith("CrossAttn") else None))
+        self.mid_block = _Mid(boc[-1], temb, g, eps, attn_cfg(nb - 1, boc[-1]))
+        self.up_blocks = nn.ModuleList()
+        rev = boc[::-1]
+        ch = rev[0]
+        for i, kind in enumerate(c.up_block_types):
+            prev, ch = ch, rev[i]
+            cin = rev[min(i + 1, nb - 1)]
+            self.up_blocks.append(_Up(cin, ch, prev, temb, c.layers_per_block + 1, g, eps, i != nb - 1,
+                                      attn_cfg(nb - 1 - i, ch) if kind.startswith("CrossAttn") else None))
+        self.conv_norm_out = nn.GroupNorm(g, boc[0], eps=eps)
+        self.conv_act = nn.SiLU()
+        self.conv_out = nn.Conv2d(boc[0], c.out_channels, 3, padding=1)
+        self.fused_norm_act = False
+
+    @property
+    def dtype(self):
+        return self.conv_in.weight.dtype
+
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None, attention_mask=None,
+                cross_attention_kwargs=None, added_cond_kwargs=None, down_block_additional_residuals=None,
+                mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
+                encoder_attention_mask=None, return_dict=True):
+        c = self.config
+        t = timestep
+        if not torch.is_tensor(t):
+            t = torch.tensor([t], dtype=torch.float32, device=sample.device)
+        elif t.ndim == 0:
+            t = t[None]
+        t = t.to(sample.device).expand(sample.shape[0])
+        emb = self.time_embedding(sinusoid(t, c.block_out_channels[0]).to(sample.dtype))
+        if c.addition_embed_type == "text_time":
+            text, ids = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
+            tid = sinusoid(ids.flatten(), c.addition_time_embed_dim).reshape(text.shape[0], -1)
+            emb = emb + self.add_embedding(torch.cat([text, tid.to(text.dtype)], dim=-1).to(emb.dtype))
+        x = self.conv_in(sample)
+        skips = [x]
+        for blk in self.down_blocks:
+            x, s = blk(x, emb, encoder_hidden_states)
+            skips += s
+        x = self.mid_block(x, emb, encoder_hidden_states)
+        for blk in self.up_blocks:
+            x = blk(x, skips, emb, encoder_hidden_states)
+        x = self.conv_norm_out(x)
+        if not self.fused_norm_act:
+            x = self.conv_act(x)
+        x = self.conv_out(x)
+        return UNet2DConditionOutput(x) if return_dict else (x,)

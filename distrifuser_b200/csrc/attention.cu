@@ -1,0 +1,443 @@
+// distrifuser_b200 -- fused multi-head attention over per-rank K/V segments (sm_100a: tcgen05 + TMEM + TMA).
+//
+// Replaces, for DistriSelfAttentionPP._forward (distrifuser/modules/pp/attn.py:127-153):
+//     torch.cat(full_kv) over ranks  -> the K/V tiles are TMA-loaded straight from the n per-rank segments
+//                                       (own fresh projection + peers' 1-step-stale arena slots)
+//     torch.split + view/transpose   -> tensor-map coordinates (head, row) select K at column h*d, V at C + h*d
+//     F.scaled_dot_product_attention -> S = Q K^T and O += P V as tcgen05.mma tiles, accumulators in TMEM
+// and the SDPA of DistriCrossAttentionPP.forward (attn.py:79-87) with nseg = 1, lseg = 77.
+//
+// CTA = one 128-row Q tile of one (batch, head).  192 threads:
+//   warps 0-3  softmax: thread i owns row i (= TMEM lane i): tcgen05.ld S, online softmax (exp2, lazy rescale),
+//              P written back to TMEM as fp16, O corrected in TMEM when the running max moved, epilogue O/l -> HBM
+//   warp 4     TMA producer: Q once, then K/V tiles through a 4-stage mbarrier ring; waits the peers' flags
+//   warp 5     MMA issuer (one lane): S[j&1] = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major)
+// TMEM columns: S0 [0,128) S1 [128,256) O [256,320) P [320,384)   (fp32 S/O, packed fp16 P)
+#include <cuda.h>
+
+#include "common.cuh"
+
+using namespace df;
+
+namespace {
+
+constexpr int BM = 128;      // Q rows per CTA
+constexpr int BN = 128;      // K/V rows per tile
+constexpr int HD = 64;       // padded head dim (d = 64, or d = 40 zero-filled by TMA)
+constexpr int STAGES = 4;
+constexpr int NTHREADS = 192;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256, COL_P = 320;
+constexpr uint32_t TILE_BYTES = BN * HD * 2;  // 16 KiB
+
+struct __align__(1024) Smem {
+  __half q[BM * HD];
+  __half k[STAGES][BN * HD];
+  __half v[STAGES][BN * HD];
+  uint64_t q_full;
+  uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
+  uint64_t s_full[2];
+  uint64_t p_full;
+  uint64_t pv_done;
+  uint32_t tmem_base;
+};
+
+struct SegInfo {
+  int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
+};
+
+// ----------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  uint32_t polls = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++polls & 4095u) == 0 && globaltimer_ns() - t0 > 10000000000ull) {
+      printf("distrifuser_b200 fmha: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// SWIZZLE_128B shared-memory matrix descriptor (version 1 = Blackwell)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+#define DF_R8(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
+#define DF_W8(r, o) "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
+
+// 32 lanes x 32 consecutive 32-bit columns: thread t of the warp gets lane (base_lane + t), columns [col, col+32)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : DF_R8(r, 0), DF_R8(r, 8), DF_R8(r, 16), DF_R8(r, 24)
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%32], "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31};"
+      ::DF_W8(r, 0), DF_W8(r, 8), DF_W8(r, 16), DF_W8(r, 24), "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// instruction descriptors (kind::f16, fp16 inputs, fp32 accumulate, M = 128)
+constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);               // K-major A, K-major B
+constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // B (=V) MN-major
+
+// ----------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NTHREADS, 1)
+fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
+                const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
+                int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
+                float scale_log2) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * BM, head = blockIdx.y, bat = blockIdx.z;
+  const int tps = (lseg + BN - 1) / BN;  // tiles per segment
+  const int T = nseg * tps;
+
+  if (warp == 5 && lane == 0) {
+    mbar_init(&sm.q_full, 1);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
+      mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
+    }
+    mbar_init(&sm.s_full[0], 1); mbar_init(&sm.s_full[1], 1);
+    mbar_init(&sm.p_full, 4);
+    mbar_init(&sm.pv_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 4) {
+    // =============================================================== TMA producer
+    if (lane == 0) {
+      prefetch_tmap(&tm_q);
+      prefetch_tmap(&tm_kv_own);
+      mbar_expect_tx(&sm.q_full, BM * HD * 2);
+      tma_load_4d(sm.q, &tm_q, &sm.q_full, 0, head, q0, bat);
+      uint32_t rd = 0;
+      if (nseg > 1) rd = comm.clock[1];
+      for (int j = 0; j < T; ++j) {
+        const int so = j / tps, t = j - so * tps;
+        int seg = own_seg + so;
+        if (seg >= nseg) seg -= nseg;
+        const void* map = &tm_kv_own;
+        if (seg != own_seg) {
+          const int r = segs.rank[seg];
+          if (t == 0 && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
+          map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
+        }
+        const int st = j % STAGES;
+        const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
+        mbar_wait(&sm.k_empty[st], ph ^ 1u);
+        mbar_expect_tx(&sm.k_full[st], TILE_BYTES);
+        tma_load_4d(sm.k[st], map, &sm.k_full[st], 0, head, t * BN, bat);
+        mbar_wait(&sm.v_empty[st], ph ^ 1u);
+        mbar_expect_tx(&sm.v_full[st], TILE_BYTES);
+        tma_load_4d(sm.v[st], map, &sm.v_full[st], 0, heads + head, t * BN, bat);
+      }
+    }
+  } else if (warp == 5) {
+    // =============================================================== MMA issuer (single thread)
+    if (lane == 0) {
+      const uint32_t q_addr = smem_u32(sm.q);
+      auto issue_qk = [&](int j) {
+        const int st = j % STAGES;
+        mbar_wait(&sm.k_full[st], (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(sm.k[st]);
+        const uint32_t d_tmem = tmem + ((j & 1) ? COL_S1 : COL_S0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          mma_ss(d_tmem, smem_desc(q_addr + kk * 32, 16, 1024), smem_desc(k_addr + kk * 32, 16, 1024), IDESC_S, kk > 0);
+        tc_commit(&sm.k_empty[st]);
+        tc_commit(&sm.s_full[j & 1]);
+      };
+      mbar_wait(&sm.q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);
+        const int st = j % STAGES;
+        mbar_wait(&sm.p_full, (uint32_t)j & 1u);
+        mbar_wait(&sm.v_full[st], (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(sm.v[st]);
+#pragma unroll
+        for (int kk = 0; kk < BN / 16; ++kk)
+          mma_ts(tmem + COL_O, tmem + COL_P + kk * 8, smem_desc(v_addr + kk * 2048, 16384, 1024), IDESC_PV,
+                 (j > 0 || kk > 0) ? 1u : 0u);
+        tc_commit(&sm.v_empty[st]);
+        tc_commit(&sm.pv_done);
+      }
+    }
+  } else {
+    // =============================================================== softmax / correction / epilogue (warps 0-3)
+    const int row = threadIdx.x;                                   // == TMEM lane
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    float m_ref = -INFINITY;                                       // max used as exponent reference (raw S units)
+    float l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int t = j % tps;
+      const int valid = min(BN, lseg - t * BN);
+      mbar_wait(&sm.s_full[j & 1], (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t sr[128];
+      const uint32_t s_addr = lane_base + ((j & 1) ? COL_S1 : COL_S0);
+      tmem_ld32(s_addr + 0, sr + 0);
+      tmem_ld32(s_addr + 32, sr + 32);
+      tmem_ld32(s_addr + 64, sr + 64);
+      tmem_ld32(s_addr + 96, sr + 96);
+      tmem_wait_ld();
+      if (valid < BN) {
+#pragma unroll
+        for (int c = 0; c < BN; ++c)
+          if (c >= valid) sr[c] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < BN; c += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+      }
+      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+      // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
+      float alpha = 1.f;
+      bool moved = false;
+      if ((m_new - m_ref) * scale_log2 > 8.f) {
+        alpha = ex2((m_ref - m_new) * scale_log2);
+        m_ref = m_new;
+        l *= alpha;
+        moved = true;
+      }
+      const float neg_ref = -m_ref * scale_log2;
+      uint32_t pr[64];
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < BN; c += 2) {
+        float p0 = ex2(fmaf(__uint_as_float(sr[c]), scale_log2, neg_ref));
+        float p1 = ex2(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_ref));
+        sum0 += p0; sum1 += p1;
+        pr[c >> 1] = pack_h2(p0, p1);
+      }
+      l += sum0 + sum1;
+      if (j > 0) {
+        mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, moved)) {
+          uint32_t o[64];
+          tmem_ld32(lane_base + COL_O, o);
+          tmem_ld32(lane_base + COL_O + 32, o + 32);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 64; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st32(lane_base + COL_O, o);
+          tmem_st32(lane_base + COL_O + 32, o + 32);
+        }
+      }
+      tmem_st32(lane_base + COL_P, pr);
+      tmem_st32(lane_base + COL_P + 32, pr + 32);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.p_full);
+    }
+    // ---- epilogue: O / l -> fp16 -> HBM
+    mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
+    tc_fence_after();
+    uint32_t o[64];
+    tmem_ld32(lane_base + COL_O, o);
+    tmem_ld32(lane_base + COL_O + 32, o + 32);
+    tmem_wait_ld();
+    const float inv_l = 1.f / l;
+    if (q0 + row < lq) {
+      __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d;
+      const int nvec = d / 8;
+#pragma unroll
+      for (int vq = 0; vq < HD / 8; ++vq) {
+        if (vq < nvec) {
+          int4 w;
+          w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
+          w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
+          w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
+          w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
+          st_v4(dst + vq * 8, w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ----------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 4-D view [d, nheads, rows, batch] of a row-major [batch, rows, pitch] fp16 matrix; box = [64, 1, 128, 1], 128B swizzle.
+int make_map(CUtensorMap* m, const void* base, int d, int nheads, int rows, int batch, int64_t pitch) {
+  EncodeTiledFn enc = get_encode();
+  DF_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)nheads, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)pitch * 2, (cuuint64_t)rows * pitch * 2};
+  cuuint32_t box[4] = {HD, 1, BN, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DF_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): base=%p d=%d heads=%d rows=%d batch=%d pitch=%lld", (int)r,
+             base, d, nheads, rows, batch, (long long)pitch);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t slot_bytes, int b, int lseg, int heads,
+                                   int d, void* maps_out, void* stream) {
+  static_assert(sizeof(CUtensorMap) == DF_TENSORMAP_BYTES, "tensor map size");
+  DF_REQUIRE(d == 64 || d == 40, "df_attn: head dim %d not supported (40, 64)", d);
+  DF_REQUIRE(slot_bytes >= (uint64_t)b * lseg * 2 * heads * d * 2, "df_attn_make_kvmaps: slot too small");
+  CUtensorMap host[DF_NBANKS * DF_MAX_WORLD];
+  memset(host, 0, sizeof(host));
+  const int64_t pitch = 2 * (int64_t)heads * d;
+  for (int k = 0; k < DF_NBANKS; ++k)
+    for (int s = 0; s < comm.world; ++s) {
+      const char* base = (const char*)comm.base[comm.rank] + (uint64_t)k * comm.bank_stride + tensor_off + (uint64_t)s * slot_bytes;
+      if (int rc = make_map(&host[k * comm.world + s], base, d, 2 * heads, lseg, b, pitch)) return rc;
+    }
+  DF_CHECK_CUDA(cudaMemcpyAsync(maps_out, host, sizeof(CUtensorMap) * DF_NBANKS * comm.world, cudaMemcpyHostToDevice,
+                                (cudaStream_t)stream));
+  DF_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps, int b, int lq,
+                           int lseg, int heads, int d, int64_t q_pitch, int64_t kv_pitch, int64_t o_pitch, int nseg,
+                           int own_seg, const int32_t* seg_rank_host, int idx, int wait_flags, float scale, void* stream) {
+  DF_REQUIRE(d == 64 || d == 40, "df_attn_fwd: head dim %d not supported (40, 64)", d);
+  DF_REQUIRE(nseg >= 1 && nseg <= DF_MAX_WORLD && own_seg >= 0 && own_seg < nseg, "df_attn_fwd: bad segment layout");
+  DF_REQUIRE(nseg == 1 || kvmaps != nullptr, "df_attn_fwd: peer segments need tensor maps (df_attn_make_kvmaps)");
+  DF_REQUIRE(q_pitch % 8 == 0 && kv_pitch % 8 == 0 && o_pitch % 8 == 0 && ((uintptr_t)q % 16) == 0 &&
+                 ((uintptr_t)kv_own % 16) == 0 && ((uintptr_t)out % 16) == 0,
+             "df_attn_fwd: q/kv/out must be 16-byte aligned with pitches multiple of 8");
+  DF_REQUIRE(b >= 1 && lq >= 1 && lseg >= 1 && heads >= 1 && heads <= 65535 && b <= 65535, "df_attn_fwd: bad shape");
+  CUtensorMap tq, tkv;
+  if (int rc = make_map(&tq, q, d, heads, lq, b, q_pitch)) return rc;
+  if (int rc = make_map(&tkv, kv_own, d, 2 * heads, lseg, b, kv_pitch)) return rc;
+  SegInfo segs;
+  for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
+  static bool attr_set = false;
+  const size_t smem_bytes = sizeof(Smem) + 1024;
+  if (!attr_set) {
+    DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    attr_set = true;
+  }
+  const float sc = (scale > 0.f ? scale : 1.f / sqrtf((float)d)) * 1.4426950408889634f;
+  dim3 grid((lq + BM - 1) / BM, heads, b);
+  fmha_fwd_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tq, tkv, (const CUtensorMap*)kvmaps, comm, segs,
+                                                                       (__half*)out, lq, lseg, heads, d, o_pitch, nseg,
+                                                                       own_seg, idx, wait_flags, sc);
+  DF_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,250 @@
+// distrifuser_b200 -- GroupNorm with cross-rank sufficient statistics (NHWC fp16).
+// Replaces DistriGroupNorm.forward (distrifuser/modules/pp/groupnorm.py:14-97): the ~10 eager reduction /
+// elementwise kernels and the 256-byte NCCL all_gather / all_reduce per layer become
+//   (1) gn_stats_kernel    one HBM read, fp32 per-channel register accumulation, per-CTA partial moments
+//   (2) gn_exchange_kernel one CTA: reduces the partials, exchanges (E[x], E[x^2]) with the patch group through
+//                          peer stores + release/acquire flags over NVLink, applies the mode formula
+//   (3) gn_apply_kernel    one read (L2-resident for <= ~60 MB activations) + one write, optional fused SiLU
+#include "common.cuh"
+
+using namespace df;
+
+namespace {
+
+struct GnPlan {
+  int V;        // 16-byte channel vectors per pixel (C/8)
+  int lanes;    // pixels processed concurrently by one CTA
+  int threads;  // blockDim
+  int nchunk;   // CTAs per sample
+  int ppc;      // pixels per CTA
+};
+
+inline GnPlan gn_plan(int b, int h, int w, int C) {
+  GnPlan p;
+  p.V = C / 8;
+  p.lanes = 512 / p.V;
+  if (p.lanes < 1) p.lanes = 1;
+  int active = p.lanes * p.V;
+  p.threads = (active + 31) / 32 * 32;
+  int hw = h * w;
+  int want = (2 * 148 + b - 1) / b;                  // ~2 CTAs per SM over the batch
+  int cap = hw / (p.lanes * 8);                      // >= 8 pixels per thread
+  if (cap < 1) cap = 1;
+  p.nchunk = want < cap ? want : cap;
+  p.ppc = (hw + p.nchunk - 1) / p.nchunk;
+  p.nchunk = (hw + p.ppc - 1) / p.ppc;
+  return p;
+}
+
+__device__ __forceinline__ void unpack8(const int4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, int hw,
+                                                       int C, int G, int V, int lanes, int ppc) {
+  extern __shared__ float acc[];  // [G][2]
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * G; i += blockDim.x) acc[i] = 0.f;
+  __syncthreads();
+  const int v = tid % V, pl = tid / V;
+  if (pl < lanes) {
+    const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
+    const __half* base = x + ((size_t)b * hw) * C + (size_t)v * 8;
+    float s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+      int4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = ld_nc_v4(base + (size_t)(p + u * lanes) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+      }
+    }
+    for (; p < p1; p += lanes) {
+      float f[8];
+      unpack8(ld_nc_v4(base + (size_t)p * C), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+    }
+    // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
+    const int cpg = C / G;
+    int g_run = (v * 8) / cpg;
+    float rs = 0.f, rss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int g = (v * 8 + j) / cpg;
+      if (g != g_run) {
+        atomicAdd(&acc[2 * g_run], rs);
+        atomicAdd(&acc[2 * g_run + 1], rss);
+        g_run = g; rs = 0.f; rss = 0.f;
+      }
+      rs += s[j]; rss += ss[j];
+    }
+    atomicAdd(&acc[2 * g_run], rs);
+    atomicAdd(&acc[2 * g_run + 1], rss);
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += blockDim.x)
+    partial[((size_t)b * nchunk + chunk) * G + g] = make_float2(acc[2 * g], acc[2 * g + 1]);
+}
+
+// mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
+__global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const float2* __restrict__ partial,
+                                                          float2* __restrict__ coef, int bG, int G, int nchunk,
+                                                          float inv_ne, float bessel, float eps, int mode, int neg_fb,
+                                                          int idx, uint64_t tensor_off, uint64_t slot_bytes,
+                                                          uint32_t group_mask) {
+  extern __shared__ float2 mine[];  // [bG]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < bG; i += blockDim.x) {
+    int b = i / G, g = i - b * G;
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < nchunk; ++k) {
+      float2 p = partial[((size_t)b * nchunk + k) * G + g];
+      s += p.x; ss += p.y;
+    }
+    mine[i] = make_float2(s * inv_ne, ss * inv_ne);
+  }
+  __syncthreads();
+  const int n = __popc(group_mask);
+  uint32_t pub = 0, rd = 0;
+  if (mode != 0) { pub = c.clock[0]; rd = c.clock[1]; }
+
+  auto publish = [&]() {
+    for (int p = 0; p < c.world; ++p) {
+      if (!(group_mask >> p & 1)) continue;
+      float2* dst = (float2*)slot_ptr(c, p, pub, tensor_off, slot_bytes, c.rank);
+      for (int i = tid; i < bG; i += blockDim.x) dst[i] = mine[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < c.world && (group_mask >> tid & 1)) st_release_sys(c.flags[tid] + (size_t)idx * c.world + c.rank, pub);
+  };
+  auto wait_all = [&]() {
+    if (tid < c.world && (group_mask >> tid & 1)) spin_until(c.flags[c.rank] + (size_t)idx * c.world + tid, rd);
+    __syncthreads();
+  };
+
+  if (mode == 1) publish();          // fresh statistics are needed by everyone in this very step
+  if (mode != 0) wait_all();         // sync: this epoch's; async: the previous epoch's (1-step stale)
+
+  for (int i = tid; i < bG; i += blockDim.x) {
+    float2 m = mine[i];
+    float mean = m.x, msq = m.y;
+    if (mode != 0) {
+      float sx = 0.f, sy = 0.f;
+      float2 own_stale = make_float2(0.f, 0.f);
+      for (int p = 0; p < c.world; ++p) {
+        if (!(group_mask >> p & 1)) continue;
+        float2 v = ((const float2*)slot_ptr(c, c.rank, rd, tensor_off, slot_bytes, p))[i];
+        if (p == c.rank) own_stale = v;
+        sx += v.x; sy += v.y;
+      }
+      const float invn = 1.f / (float)n;
+      if (mode == 1) { mean = sx * invn; msq = sy * invn; }                                     // groupnorm.py:47,80
+      else if (mode == 2) { mean = sx * invn + (m.x - own_stale.x); msq = sy * invn + (m.y - own_stale.y); }  // :49-51
+      else { mean = (sx - own_stale.x + m.x) * invn; msq = (sy - own_stale.y + m.y) * invn; }  // :52-55
+    }
+    float var = msq - mean * mean;
+    if (neg_fb && var < 0.f) var = m.y - m.x * m.x;                                             // :60-63
+    var *= bessel;                                                                              // :65-66
+    coef[i] = make_float2(mean, rsqrtf(var + eps));
+  }
+  if (mode >= 2) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
+}
+
+__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                       const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                                       const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
+                                                       int ppc, int silu) {
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int v = tid % V, pl = tid / V;
+  if (pl >= lanes) return;
+  const int cpg = C / G;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = v * 8 + j;
+    float2 mr = coef[b * G + ch / cpg];
+    float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
+    sc[j] = mr.y * ga;
+    sh[j] = be - mr.x * sc[j];
+  }
+  const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
+  const size_t base = ((size_t)b * hw) * C + (size_t)v * 8;
+  auto xform = [&](const int4& in) {
+    float f[8];
+    unpack8(in, f);
+    int4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(f[j], sc[j], sh[j]);
+      if (silu) t = __fdividef(t, 1.f + __expf(-t));
+      f[j] = t;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+    return o;
+  };
+  int p = p0 + pl;
+  for (; p + 3 * lanes < p1; p += 4 * lanes) {
+    int4 r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = ld_nc_v4(x + base + (size_t)(p + u * lanes) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st_v4(y + base + (size_t)(p + u * lanes) * C, xform(r[u]));
+  }
+  for (; p < p1; p += lanes) st_v4(y + base + (size_t)p * C, xform(ld_nc_v4(x + base + (size_t)p * C)));
+}
+
+}  // namespace
+
+extern "C" size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, int C) {
+  GnPlan p = gn_plan(b, h, w, C);
+  return ((size_t)b * p.nchunk * groups + (size_t)b * groups) * sizeof(float2) + 256;
+}
+
+extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, void* y, const void* gamma, const void* beta, int b,
+                                int h, int w, int C, int groups, float eps, int mode, int bessel, int neg_var_fallback,
+                                int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes, uint32_t group_mask,
+                                void* scratch, void* stream) {
+  DF_REQUIRE(C % 8 == 0 && C % groups == 0 && C / 8 <= 512, "df_groupnorm_fwd: unsupported channel count %d", C);
+  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "df_groupnorm_fwd: x/y must be 16-byte aligned");
+  DF_REQUIRE(mode >= 0 && mode <= 3, "df_groupnorm_fwd: bad mode %d", mode);
+  DF_REQUIRE(mode == 0 || (slot_bytes >= (uint64_t)b * groups * 8 && (group_mask >> comm.rank & 1)),
+             "df_groupnorm_fwd: statistics slot too small or rank outside its own group");
+  cudaStream_t st = (cudaStream_t)stream;
+  GnPlan p = gn_plan(b, h, w, C);
+  float2* partial = (float2*)scratch;
+  float2* coef = partial + (size_t)b * p.nchunk * groups;
+  const int hw = h * w;
+  const long long ne = (long long)(C / groups) * hw;
+  gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, 2 * groups * sizeof(float), st>>>((const __half*)x, partial, hw, C,
+                                                                                   groups, p.V, p.lanes, p.ppc);
+  DF_CHECK_LAUNCH();
+  float bess = bessel ? (float)((double)ne / (double)(ne - 1)) : 1.f;
+  gn_exchange_kernel<<<1, 256, (size_t)b * groups * sizeof(float2), st>>>(
+      comm, partial, coef, b * groups, groups, p.nchunk, (float)(1.0 / (double)ne), bess, eps, mode, neg_var_fallback, idx,
+      tensor_off, slot_bytes, group_mask);
+  DF_CHECK_LAUNCH();
+  gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (__half*)y, (const __half*)gamma,
+                                                           (const __half*)beta, coef, hw, C, groups, p.V, p.lanes, p.ppc,
+                                                           fuse_silu);
+  DF_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,120 @@
+"""DistriSelfAttentionPP / DistriCrossAttentionPP -- drop-ins for distrifuser/modules/pp/attn.py:12-195.
+
+q / fused kv / out projections stay library GEMMs (cuBLAS through F.linear); everything between them --
+the reference's torch.cat of the per-rank K/V (attn.py:131-138), split / view / transpose (:142-149) and
+F.scaled_dot_product_attention (:153) -- is one tcgen05 kernel (df_attn_fwd) that TMA-loads the K/V tiles
+straight from the n per-rank segments: this rank's fresh projection and the peers' 1-step-stale arena slots."""
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ... import _lib
+from ...utils import DistriConfig
+from ..base_module import BaseModule
+
+
+class DistriAttentionPP(BaseModule):
+    def __init__(self, module: nn.Module, distri_config: DistriConfig):
+        super().__init__(module, distri_config)
+        to_k, to_v = module.to_k, module.to_v                            # attn.py:16-21
+        assert isinstance(to_k, nn.Linear) and isinstance(to_v, nn.Linear)
+        assert (to_k.bias is None) == (to_v.bias is None)
+        assert to_k.weight.shape == to_v.weight.shape
+        in_size, out_size = to_k.in_features, to_k.out_features
+        to_kv = nn.Linear(in_size, out_size * 2, bias=to_k.bias is not None, device=to_k.weight.device,
+                          dtype=to_k.weight.dtype)                       # attn.py:23-39 (K | V fused)
+        with torch.no_grad():
+            to_kv.weight[:out_size].copy_(to_k.weight)
+            to_kv.weight[out_size:].copy_(to_v.weight)
+            if to_k.bias is not None:
+                to_kv.bias[:out_size].copy_(to_k.bias)
+                to_kv.bias[out_size:].copy_(to_v.bias)
+        self.to_kv = to_kv
+        self._kvmaps = None
+
+    def _attend(self, q, kv_own, lseg, nseg, own_seg, wait_flags):
+        """softmax(q k^T / sqrt(d)) v over `nseg` K/V segments of `lseg` rows each; q:[b,lq,C], kv_own:[b,lseg,2C]."""
+        attn = self.module
+        b, lq, Cq = q.shape
+        heads = attn.heads
+        d = Cq // heads
+        out = torch.empty_like(q)
+        cm = self.comm_manager
+        if nseg > 1:
+            comm, maps = cm.group, self._kvmaps.data_ptr()
+        else:
+            comm, maps = _lib.null_comm(), None
+        seg_rank = (C.c_int32 * _lib.MAX_WORLD)(*range(_lib.MAX_WORLD))
+        _lib.check(_lib.lib().df_attn_fwd(comm, q.data_ptr(), kv_own.data_ptr(), out.data_ptr(), maps, b, lq, lseg,
+                                          heads, d, q.stride(1), kv_own.stride(1), out.stride(1), nseg, own_seg,
+                                          seg_rank, self.idx or 0, int(wait_flags), 0.0,
+                                          torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+        return out
+
+    def _project_out(self, hidden_states, residual):
+        attn = self.module
+        hidden_states = attn.to_out[0](hidden_states)                    # attn.py:93-96 / 158-161
+        hidden_states = attn.to_out[1](hidden_states)
+        if attn.residual_connection:
+            hidden_states = hidden_states + residual
+        if attn.rescale_output_factor != 1.0:
+            hidden_states = hidden_states / attn.rescale_output_factor
+        return hidden_states
+
+
+class DistriCrossAttentionPP(DistriAttentionPP):
+    def __init__(self, module: nn.Module, distri_config: DistriConfig):
+        super().__init__(module, distri_config)
+        self.kv_cache = None
+
+    def forward(self, hidden_states, encoder_hidden_states=None, scale: float = 1.0, *args, **kwargs):
+        assert encoder_hidden_states is not None                         # attn.py:55
+        self._require_cuda_half(hidden_states, "DistriCrossAttentionPP")
+        attn = self.module
+        q = attn.to_q(hidden_states)
+        if self.counter == 0 or self.kv_cache is None:                   # attn.py:56,73-77: text K/V once per image
+            kv = self.to_kv(encoder_hidden_states)
+            if self.kv_cache is not None and self.kv_cache.shape == kv.shape:
+                self.kv_cache.copy_(kv)                                  # stable address for captured graphs
+            else:
+                self.kv_cache = kv
+        kv = self.kv_cache
+        out = self._attend(q, kv, kv.shape[1], 1, 0, False)
+        out = self._project_out(out, hidden_states)
+        self.counter += 1
+        return out
+
+
+class DistriSelfAttentionPP(DistriAttentionPP):
+    def forward(self, hidden_states, encoder_hidden_states=None, scale: float = 1.0, *args, **kwargs):
+        cfg = self.distri_config
+        self._require_cuda_half(hidden_states, "DistriSelfAttentionPP")
+        attn = self.module
+        n, r = cfg.n_device_per_batch, cfg.split_idx()
+        b, l, c = hidden_states.shape
+        cm = self.comm_manager
+        if n > 1 and self._recording() and self.idx is None:
+            self.idx = cm.register_tensor((b, l, self.to_kv.out_features), hidden_states.dtype, layer_type="attn")  # :185-190
+        q = attn.to_q(hidden_states)                                     # attn.py:121
+        kv = self.to_kv(hidden_states)                                   # attn.py:125
+        if n == 1 or not self._bound():
+            # attn.py:127-131: one rank, or buffers not created yet (n identical copies of kv give the same softmax)
+            out = self._attend(q, kv, l, 1, 0, False)
+        else:
+            if self._kvmaps is None:
+                self._kvmaps = torch.empty(_lib.NBANKS * n * _lib.TENSORMAP_BYTES, dtype=torch.uint8, device=q.device)
+                heads = attn.heads
+                _lib.check(_lib.lib().df_attn_make_kvmaps(cm.group, cm.tensor_off[self.idx], cm.slot_bytes[self.idx], b, l,
+                                                          heads, c // heads, self._kvmaps.data_ptr(),
+                                                          torch.cuda.current_stream().cuda_stream), "df_attn_make_kvmaps")
+            sync = cfg.mode == "full_sync" or self._is_sync_step()
+            if sync:
+                cm.enqueue(self.idx, kv, async_stream=False)             # attn.py:133: everyone needs it this step
+            elif cfg.mode != "no_sync":
+                cm.enqueue(self.idx, kv, async_stream=True)              # attn.py:139-140: hidden under the attention
+            out = self._attend(q, kv, l, n, r, True)                     # attn.py:134-153, peers' segments in place
+        out = self._project_out(out, hidden_states)
+        self.counter += 1
+        return out

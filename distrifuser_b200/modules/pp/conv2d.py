@@ -1,0 +1,73 @@
+"""DistriConv2dPP -- drop-in for distrifuser/modules/pp/conv2d.py:10-115.
+
+The halo rows go to the two patch neighbours only (df_halo_push, peer stores over NVLink) instead of an
+all_gather over every rank, and the padded conv input is assembled by one vectorised kernel
+(df_halo_assemble) instead of torch.stack + cat + F.pad.  The convolution itself stays a cuDNN library call
+on the NHWC padded tensor (SURVEY 8f N1 lists the hand-written implicit GEMM as a later row)."""
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ... import _lib
+from ...utils import DistriConfig
+from ..base_module import BaseModule
+
+
+class DistriConv2dPP(BaseModule):
+    def __init__(self, module: nn.Conv2d, distri_config: DistriConfig, is_first_layer: bool = False):
+        super().__init__(module, distri_config)
+        self.is_first_layer = is_first_layer
+
+    def naive_forward(self, x: torch.Tensor) -> torch.Tensor:        # conv2d.py:15-18
+        return self.module(x)
+
+    def sliced_forward(self, x: torch.Tensor) -> torch.Tensor:       # conv2d.py:20-41 (conv_in: 4 channels, tiny)
+        cfg = self.distri_config
+        b, c, h, w = x.shape
+        assert h % cfg.n_device_per_batch == 0
+        stride, padding = self.module.stride[0], self.module.padding[0]
+        out_h = h // stride // cfg.n_device_per_batch
+        r = cfg.split_idx()
+        lo, hi = out_h * r * stride - padding, out_h * (r + 1) * stride + padding
+        pad_t, pad_b = max(0, -lo), max(0, hi - h)
+        xs = F.pad(x[:, :, max(lo, 0):min(hi, h), :], [padding, padding, pad_t, pad_b])
+        return F.conv2d(xs, self.module.weight, self.module.bias, stride=stride, padding="valid")
+
+    def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        cfg = self.distri_config
+        n = cfg.n_device_per_batch
+        if n == 1:
+            out = self.naive_forward(x)                              # conv2d.py:51-52
+        elif self.is_first_layer:
+            out = self.sliced_forward(x)                             # conv2d.py:54-56
+        else:
+            self._require_cuda_half(x, "DistriConv2dPP")
+            p = self.module.padding[0]
+            b, c, h, w = x.shape
+            if self._recording() and self.idx is None:
+                self.idx = self.comm_manager.register_tensor([2, b, c, p, w], x.dtype, layer_type="conv2d")  # :58-65
+            if not self._bound():
+                out = self.naive_forward(x)                          # conv2d.py:68-69
+            else:
+                assert p == 1 and self.module.kernel_size[0] == 3, "halo exchange is written for 3x3 / padding 1"
+                cm = self.comm_manager
+                L = _lib.lib()
+                r = cfg.split_idx()
+                up, down = (r - 1 if r > 0 else -1), (r + 1 if r < n - 1 else -1)
+                x = x.contiguous(memory_format=torch.channels_last)
+                xp = torch.empty((b, c, h + 2, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+                st = torch.cuda.current_stream().cuda_stream
+                off, sb = cm.tensor_off[self.idx], cm.slot_bytes[self.idx]
+                sync = cfg.mode == "full_sync" or self._is_sync_step()
+                if sync:                                             # conv2d.py:92-93: fresh halos
+                    _lib.check(L.df_halo_push(cm.group, x.data_ptr(), b, h, w, c, self.idx, off, sb, up, down, st),
+                               "df_halo_push")
+                _lib.check(L.df_halo_assemble(cm.group, x.data_ptr(), xp.data_ptr(), b, h, w, c, self.idx, off, sb,
+                                              up, down, 1, st), "df_halo_assemble")
+                out = F.conv2d(xp, self.module.weight, self.module.bias, stride=self.module.stride[0],
+                               padding=(0, self.module.padding[1]))  # conv2d.py:95-110
+                if not sync and cfg.mode != "no_sync":               # conv2d.py:111-112: ship for the next step
+                    _lib.check(L.df_halo_push(cm.group, x.data_ptr(), b, h, w, c, self.idx, off, sb, up, down, st),
+                               "df_halo_push")
+        self.counter += 1
+        return out

@@ -1,0 +1,242 @@
+"""GPU parity of each sm_100a kernel through the C ABI, against fp32 torch restatements of the reference math
+(oracle/pp_modules.py for the mode formulas).  Tolerances are for fp16 storage with fp32 accumulation:
+attention 2e-3 abs on O(1) outputs (P is rounded to fp16 before PV, like every flash kernel), GroupNorm 4e-3
+(one fp16 rounding of the output), halo / publication bit-exact."""
+import ctypes as C
+
+import pytest
+import torch
+
+from helpers import LoopbackArena, sdpa_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, wait=0):
+    from distrifuser_b200 import _lib
+    b, lq, Cq = q.shape
+    d = Cq // heads
+    out = torch.empty_like(q)
+    seg_rank = (C.c_int32 * 8)(*range(8))
+    _lib.check(_lib.lib().df_attn_fwd(comm or _lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), maps, b, lq,
+                                      lseg or kv.shape[1], heads, d, q.stride(1), kv.stride(1), out.stride(1), nseg, own,
+                                      seg_rank, idx, wait, 0.0, torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("b,lq,lk,heads,d", [
+    (1, 128, 128, 1, 64),          # one tile
+    (2, 256, 384, 2, 64),          # multi-tile, multi-head, batch
+    (1, 200, 77, 2, 64),           # ragged q tile + cross-attention length (one partial K/V tile)
+    (2, 300, 1000, 3, 64),         # ragged both ways, > STAGES tiles
+    (1, 1024, 4096, 10, 64),       # SDXL level-1 shape at 1024^2, n=4 (lq=L/4)
+    (1, 130, 200, 2, 40),          # SD1.x head_dim 40 (zero-filled to 64 by TMA)
+])
+def test_attention_single_segment(b, lq, lk, heads, d):
+    torch.manual_seed(0)
+    Cq = heads * d
+    q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16)
+    kv = torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16)
+    out = _attn(q, kv, heads)
+    ref = sdpa_ref(q, kv[..., :Cq], kv[..., Cq:], heads)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+def test_attention_large_logits_rescale():
+    """Rows whose running max jumps by > 2^8 between tiles exercise the O-correction path."""
+    torch.manual_seed(1)
+    b, lq, lk, heads, d = 1, 128, 512, 1, 64
+    q = torch.randn(b, lq, d, device="cuda", dtype=torch.float16) * 4
+    kv = torch.randn(b, lk, 2 * d, device="cuda", dtype=torch.float16)
+    kv[:, 300:, :d] *= 6          # later tiles carry much larger logits
+    out = _attn(q, kv, heads)
+    ref = sdpa_ref(q, kv[..., :d], kv[..., d:], heads)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 4e-3, f"max abs err {err}"
+
+
+@pytest.mark.parametrize("n,own", [(2, 0), (2, 1), (4, 2)])
+def test_attention_multi_segment_stale_slots(n, own):
+    """K/V of the peers is read in place from the arena slots of the READ epoch (attn.py:136-138 without the cat)."""
+    from distrifuser_b200 import _lib
+    torch.manual_seed(2)
+    b, lseg, heads, d = 2, 200, 2, 64
+    Cq = heads * d
+    nbytes = b * lseg * 2 * Cq * 2
+    arena = LoopbackArena(n, [nbytes], rank=own)
+    epoch = 7
+    segs = [torch.randn(b, lseg, 2 * Cq, device="cuda", dtype=torch.float16) for _ in range(n)]
+    for s in range(n):
+        if s != own:
+            arena.slot(epoch, 0, s, nbytes).copy_(segs[s].flatten())
+            arena.slot(epoch + 1, 0, s, nbytes).fill_(float("nan"))     # a different bank must not be touched
+            arena.flags[0, s] = epoch
+    arena.set_clock(pub=epoch + 1, rd=epoch)
+    maps = torch.empty(_lib.NBANKS * n * _lib.TENSORMAP_BYTES, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().df_attn_make_kvmaps(arena.comm, arena.tensor_off[0], arena.slot_bytes[0], b, lseg, heads, d,
+                                              maps.data_ptr(), torch.cuda.current_stream().cuda_stream), "kvmaps")
+    q = torch.randn(b, 300, Cq, device="cuda", dtype=torch.float16)
+    out = _attn(q, segs[own], heads, comm=arena.comm, maps=maps.data_ptr(), nseg=n, own=own, lseg=lseg, wait=1)
+    full = torch.cat(segs, 1)
+    ref = sdpa_ref(q, full[..., :Cq], full[..., Cq:], heads)
+    err = (out.float() - ref).abs().max().item()
+    arena.close()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+def _gn_ref(x, G, w, b_, eps, mean, meansq, bessel=True, silu=False):
+    B, Cc, H, W = x.shape
+    x5 = x.float().view(B, G, Cc // G, H, W)
+    var = meansq - mean * mean
+    ne = (Cc // G) * H * W
+    if bessel:
+        var = var * (ne / (ne - 1))
+    y = ((x5 - mean) / (var + eps).sqrt()).view(B, Cc, H, W) * w.float().view(1, -1, 1, 1) + b_.float().view(1, -1, 1, 1)
+    return torch.nn.functional.silu(y) if silu else y
+
+
+def _moments(x, G):
+    B, Cc, H, W = x.shape
+    x5 = x.float().view(B, G, Cc // G, H, W)
+    return x5.mean(dim=[2, 3, 4], keepdim=True), (x5 * x5).mean(dim=[2, 3, 4], keepdim=True)
+
+
+def _gn_call(x, G, w, b_, eps, mode, bessel, negfb, silu, comm, idx, off, sb, mask):
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    B, Cc, H, W = x.shape
+    y = torch.empty_like(x, memory_format=torch.channels_last)
+    scratch = torch.empty(L.df_groupnorm_scratch_bytes(B, G, H, W, Cc), dtype=torch.uint8, device="cuda")
+    _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), y.data_ptr(), w.data_ptr(), b_.data_ptr(), B, H, W, Cc, G, eps, mode,
+                                  bessel, negfb, silu, idx, off, sb, mask, scratch.data_ptr(),
+                                  torch.cuda.current_stream().cuda_stream), "df_groupnorm_fwd")
+    torch.cuda.synchronize()
+    return y
+
+
+@pytest.mark.parametrize("B,Cc,H,W,G", [(2, 320, 32, 32, 32), (1, 640, 16, 24, 32), (2, 960, 8, 8, 32), (1, 1280, 15, 60, 32),
+                                       (2, 64, 8, 16, 32), (1, 2560, 4, 8, 32), (1, 80, 6, 10, 8)])
+@pytest.mark.parametrize("silu", [0, 1])
+def test_groupnorm_local(B, Cc, H, W, G, silu):
+    from distrifuser_b200 import _lib
+    torch.manual_seed(3)
+    x = (torch.randn(B, Cc, H, W, device="cuda") * 2 + 0.5).half().contiguous(memory_format=torch.channels_last)
+    w = (1 + 0.1 * torch.randn(Cc, device="cuda")).half()
+    b_ = (0.1 * torch.randn(Cc, device="cuda")).half()
+    y = _gn_call(x, G, w, b_, 1e-5, 0, 0, 0, silu, _lib.null_comm(), 0, 0, 0, 1)
+    m, m2 = _moments(x, G)
+    ref = _gn_ref(x, G, w, b_, 1e-5, m, m2, bessel=False, silu=bool(silu))
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    err = (y.float() - ref).abs().max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item() / 4), f"max abs err {err}"
+
+
+@pytest.mark.parametrize("mode_name", ["sync", "corrected_async_gn", "stale_gn"])
+def test_groupnorm_exchange_modes(mode_name):
+    """Mode formulas of groupnorm.py:45-56 with n=2 ranks emulated in one arena (this rank = 0)."""
+    torch.manual_seed(4)
+    B, Cc, H, W, G, n = 2, 320, 8, 16, 32, 2
+    nb = B * G * 8
+    arena = LoopbackArena(n, [nb], rank=0)
+    w = (1 + 0.1 * torch.randn(Cc, device="cuda")).half()
+    b_ = (0.1 * torch.randn(Cc, device="cuda")).half()
+    x_now = (torch.randn(B, Cc, H, W, device="cuda") + 0.3).half().contiguous(memory_format=torch.channels_last)
+    x_peer = (torch.randn(B, Cc, H, W, device="cuda") * 1.5).half()
+    x_old = (torch.randn(B, Cc, H, W, device="cuda") * 0.7 - 0.2).half()      # this rank's previous-step activation
+    pack = lambda m, m2: torch.stack([m.flatten(), m2.flatten()], -1).contiguous()
+    mine = _moments(x_now, G); peer = _moments(x_peer, G); old = _moments(x_old, G)
+    epoch = 5
+    if mode_name == "sync":
+        arena.slot(epoch, 0, 1, nb, torch.float32).copy_(pack(*peer).flatten())
+        arena.flags[0, 1] = epoch
+        arena.set_clock(pub=epoch, rd=epoch)
+        mode, negfb = 1, 0
+        mean, msq = (mine[0] + peer[0]) / 2, (mine[1] + peer[1]) / 2
+    else:
+        arena.slot(epoch, 0, 1, nb, torch.float32).copy_(pack(*peer).flatten())
+        arena.slot(epoch, 0, 0, nb, torch.float32).copy_(pack(*old).flatten())
+        arena.flags[0, 0] = epoch; arena.flags[0, 1] = epoch
+        arena.set_clock(pub=epoch + 1, rd=epoch)
+        if mode_name == "corrected_async_gn":
+            mode, negfb = 2, 1
+            mean = (old[0] + peer[0]) / 2 + (mine[0] - old[0]); msq = (old[1] + peer[1]) / 2 + (mine[1] - old[1])
+            var = msq - mean * mean
+            msq = torch.where(var < 0, mine[1] - mine[0] ** 2 + mean * mean, msq)   # groupnorm.py:60-63 as an E[x^2] patch
+        else:
+            mode, negfb = 3, 0
+            mean, msq = (mine[0] + peer[0]) / 2, (mine[1] + peer[1]) / 2
+    y = _gn_call(x_now, G, w, b_, 1e-5, mode, 1, negfb, 0, arena.comm, 0, arena.tensor_off[0], arena.slot_bytes[0], 0b11)
+    ref = _gn_ref(x_now, G, w, b_, 1e-5, mean, msq, bessel=True)
+    err = (y.float() - ref).abs().max().item()
+    # the kernel must also have published this step's statistics (slot src=0 of the pub bank) and stamped its flag
+    pub = epoch if mode_name == "sync" else epoch + 1
+    got = arena.slot(pub, 0, 0, nb, torch.float32).view(B * G, 2)
+    pub_err = (got - pack(*mine)).abs().max().item()
+    flag = int(arena.flags[0, 0].item())
+    arena.close()
+    assert err < 6e-3, f"max abs err {err}"
+    assert pub_err < 1e-4 and flag == pub
+
+
+@pytest.mark.parametrize("up,down", [(-1, 1), (0, 2), (2, -1)])
+def test_halo_push_and_assemble(up, down):
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(5)
+    b, c, h, w, n = 2, 64, 6, 10, 4
+    rank = 1 if up == 0 else (0 if up < 0 else 3)
+    row_bytes = w * c * 2
+    arena = LoopbackArena(n, [2 * b * row_bytes], rank=rank)
+    x = torch.randn(b, c, h, w, device="cuda").half().contiguous(memory_format=torch.channels_last)
+    epoch = 9
+    arena.set_clock(pub=epoch, rd=epoch)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.df_halo_push(arena.comm, x.data_ptr(), b, h, w, c, 0, arena.tensor_off[0], arena.slot_bytes[0], up, down, st), "push")
+    torch.cuda.synchronize()
+    # loopback: what this rank pushed sits in slot src=rank; part 0 = first rows, part 1 = last rows (conv2d.py:90)
+    mine = arena.slot(epoch, 0, rank, 2 * b * row_bytes).view(2, b, w, c)
+    xn = x.permute(0, 2, 3, 1)                       # [b,h,w,c] view of the NHWC memory
+    if up >= 0:
+        assert torch.equal(mine[0], xn[:, 0])
+    if down >= 0:
+        assert torch.equal(mine[1], xn[:, -1])
+    # neighbours' rows for the assemble step
+    top_src = torch.randn(b, w, c, device="cuda").half()
+    bot_src = torch.randn(b, w, c, device="cuda").half()
+    if up >= 0:
+        arena.slot(epoch, 0, up, 2 * b * row_bytes).view(2, b, w, c)[1].copy_(top_src)
+        arena.flags[0, up] = epoch
+    if down >= 0:
+        arena.slot(epoch, 0, down, 2 * b * row_bytes).view(2, b, w, c)[0].copy_(bot_src)
+        arena.flags[0, down] = epoch
+    xp = torch.empty((b, c, h + 2, w), dtype=torch.float16, device="cuda", memory_format=torch.channels_last)
+    _lib.check(L.df_halo_assemble(arena.comm, x.data_ptr(), xp.data_ptr(), b, h, w, c, 0, arena.tensor_off[0], arena.slot_bytes[0],
+                                  up, down, 1, st), "assemble")
+    torch.cuda.synchronize()
+    xpn = xp.permute(0, 2, 3, 1)
+    ok = torch.equal(xpn[:, 1:-1], xn)
+    ok &= torch.equal(xpn[:, 0], top_src if up >= 0 else torch.zeros_like(top_src))
+    ok &= torch.equal(xpn[:, -1], bot_src if down >= 0 else torch.zeros_like(bot_src))
+    arena.close()
+    assert ok
+
+
+def test_publish_and_wait_roundtrip():
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    n, nbytes = 4, 3 * 1000 * 256 * 2
+    arena = LoopbackArena(n, [nbytes, nbytes], rank=2)
+    src = torch.randn(3, 1000, 256, device="cuda").half()
+    arena.set_clock(pub=4, rd=4)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.df_slot_publish(arena.comm, src.data_ptr(), 1, nbytes, nbytes, arena.tensor_off[1], arena.slot_bytes[1], 1,
+                                 0b1011, 16, st), "publish")
+    _lib.check(L.df_slot_wait(arena.comm, 1, 0b0100, st), "wait")      # own flag: set by the publish above
+    torch.cuda.synchronize()
+    got = arena.slot(4, 1, 2, nbytes).view(3, 1000, 256)
+    flag = int(arena.flags[1, 2].item())
+    ok = torch.equal(got, src)
+    arena.close()
+    assert ok and flag == 4

@@ -65,7 +65,15 @@ def lib():
     return _lib
 
 
+# kernels launched per C-ABI call (bench.py reports the count of OUR launches inside the timed region)
+KERNELS_PER_CALL = {"df_groupnorm_fwd": 3, "df_attn_fwd": 1, "df_halo_push": 1, "df_halo_assemble": 1,
+                    "df_slot_publish": 1, "df_slot_wait": 1, "df_step_begin": 1, "df_output_gather": 2}
+LAUNCHES = {"total": 0}
+PROFILE = None   # bench.py sets this to a list; kernels then bracket their launch with CUDA events on the launching stream
+
+
 def check(rc: int, what: str = ""):
+    LAUNCHES["total"] += KERNELS_PER_CALL.get(what, 0)
     if rc != 0:
         raise RuntimeError(f"distrifuser_b200 {what} failed ({rc}): {lib().df_last_error().decode()}")
 

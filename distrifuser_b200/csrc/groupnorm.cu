@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const flo
   const int n = __popc(group_mask);
   uint32_t pub = 0, rd = 0;
   if (mode != 0) { pub = c.clock[0]; rd = c.clock[1]; }
+  if (mode == 1) rd = pub;  // a synchronous exchange reads THIS epoch even inside an asynchronous step (sync_gn, groupnorm.py:74-80)
 
   auto publish = [&]() {
     for (int p = 0; p < c.world; ++p) {

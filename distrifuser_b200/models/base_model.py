@@ -19,6 +19,7 @@ class BaseModel(nn.Module):
         self.static_inputs = None
         self.static_outputs = None
         self.cuda_graphs = None
+        self.graph_launches = None       # number of this package's kernels inside each captured graph
 
     def forward(self, *args, **kwargs):
         raise NotImplementedError
@@ -35,9 +36,10 @@ class BaseModel(nn.Module):
             if isinstance(module, BaseModule):
                 module.set_comm_manager(comm_manager)
 
-    def setup_cuda_graph(self, static_outputs, cuda_graphs):       # base_model.py:39-41
+    def setup_cuda_graph(self, static_outputs, cuda_graphs, graph_launches=None):   # base_model.py:39-41
         self.static_outputs = static_outputs
         self.cuda_graphs = cuda_graphs
+        self.graph_launches = graph_launches
 
     @property
     def config(self):

@@ -121,6 +121,8 @@ class DistriUNetPP(BaseModel):  # for Patch Parallelism
             else:
                 graph_idx = 2
             self.cuda_graphs[graph_idx].replay()
+            if self.graph_launches is not None:
+                _lib.LAUNCHES["total"] += self.graph_launches[graph_idx]
             output = self.static_outputs[graph_idx]
         else:
             cm = self.comm_manager

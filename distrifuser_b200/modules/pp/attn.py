@@ -34,7 +34,7 @@ class DistriAttentionPP(BaseModule):
         self.to_kv = to_kv
         self._kvmaps = None
 
-    def _attend(self, q, kv_own, lseg, nseg, own_seg, wait_flags):
+    def _attend(self, q, kv_own, lseg, nseg, own_seg, wait_flags, kind="self"):
         """softmax(q k^T / sqrt(d)) v over `nseg` K/V segments of `lseg` rows each; q:[b,lq,C], kv_own:[b,lseg,2C]."""
         attn = self.module
         b, lq, Cq = q.shape
@@ -47,10 +47,19 @@ class DistriAttentionPP(BaseModule):
         else:
             comm, maps = _lib.null_comm(), None
         seg_rank = (C.c_int32 * _lib.MAX_WORLD)(*range(_lib.MAX_WORLD))
+        prof = _lib.PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(_lib.lib().df_attn_fwd(comm, q.data_ptr(), kv_own.data_ptr(), out.data_ptr(), maps, b, lq, lseg,
                                           heads, d, q.stride(1), kv_own.stride(1), out.stride(1), nseg, own_seg,
                                           seg_rank, self.idx or 0, int(wait_flags), 0.0,
                                           torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+        if prof is not None:
+            e1.record()
+            prof.append(dict(kernel="fmha_fwd_kernel", kind=kind,
+                             flops=4.0 * b * lq * nseg * lseg * Cq, bytes=2.0 * (2 * b * lq * Cq + b * nseg * lseg * 2 * Cq),
+                             shape=(b, lq, nseg * lseg, heads, d), start=e0, end=e1))
         return out
 
     def _project_out(self, hidden_states, residual):
@@ -81,7 +90,7 @@ class DistriCrossAttentionPP(DistriAttentionPP):
             else:
                 self.kv_cache = kv
         kv = self.kv_cache
-        out = self._attend(q, kv, kv.shape[1], 1, 0, False)
+        out = self._attend(q, kv, kv.shape[1], 1, 0, False, kind="cross")
         out = self._project_out(out, hidden_states)
         self.counter += 1
         return out

@@ -63,9 +63,17 @@ class DistriGroupNorm(BaseModule):
             comm, off, sb, mask = _lib.null_comm(), 0, 0, 1
         gamma = module.weight.data_ptr() if module.affine else None
         beta = module.bias.data_ptr() if module.affine else None
+        prof = _lib.PROFILE
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
                                       mode, bessel, neg_fb, int(self.fuse_silu), self.idx or 0, off, sb, mask,
                                       self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
                    "df_groupnorm_fwd")
+        if prof is not None:
+            e1.record()
+            prof.append(dict(kernel="groupnorm", kind="gn", flops=0.0, bytes=4.0 * x.numel(), shape=tuple(x.shape),
+                             start=e0, end=e1))
         self.counter += 1
         return y

@@ -72,15 +72,19 @@ class _DistriPipelineBase:
             # same static input tensors for every graph (the wrapper slices the CFG batch before recording)
             unet.static_inputs = None
             pool = None
+            from . import _lib
+            launches = []
             for counter in counters:
                 graph = torch.cuda.CUDAGraph()
+                n0 = _lib.LAUNCHES["total"]
                 with torch.cuda.graph(graph, pool=pool):
                     unet.set_counter(counter)
                     output = unet(**static_inputs, return_dict=False, record=True)[0]
                     static_outputs.append(output)
+                launches.append(_lib.LAUNCHES["total"] - n0)
                 pool = graph.pool()
                 cuda_graphs.append(graph)
-            unet.setup_cuda_graph(static_outputs, cuda_graphs)
+            unet.setup_cuda_graph(static_outputs, cuda_graphs, launches)
         self.static_inputs = static_inputs
         self.comm_manager = comm_manager
 

@@ -64,7 +64,7 @@ class UNetCase:
     warmup_steps: int = 1
     steps: int = 4
     latent: int = 32                 # latent side S (image side = 8*S)
-    comm_checkpoint: int = 60
+    comm_checkpoint: int = 20        # <= registered tensors in every mode (SURVEY D-13): every module sees 1-step-stale data, as in SDXL / SD1.x
     weight_seed: int = 0
     input_seed: int = 1234
 

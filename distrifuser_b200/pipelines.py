@@ -52,6 +52,9 @@ class _DistriPipelineBase:
         assert cfg.height % 8 == 0 and cfg.width % 8 == 0
         static_inputs = self._static_inputs(**kwargs)
         unet = pipeline.unet
+        # cuDNN heuristics pick legacy sm80 "wo_smem" implicit-GEMM kernels for several 3x3 shapes on sm_100
+        # (profiles/r1_launches_1024.md); autotuning happens in the un-captured passes below
+        torch.backends.cudnn.benchmark = True
         comm_manager = None
         # the reference creates the manager only for n_device_per_batch > 1 (pipelines.py:132); the final epsilon
         # gather also goes through the arena here, so any world_size > 1 needs one

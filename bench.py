@@ -209,6 +209,19 @@ def run_ours(a):
     ms_image = total_ms / a.steps
     ms_image_e2e = e2e_ms / a.steps
 
+    # ---- exposed communication: same kernels with every publication / peer wait removed after warm-up
+    #      (mode "no_sync" = compute-only lower bound); (t(mode) - t(no_sync)) / t(mode)
+    exposed = None
+    if world > 1 and cfg.n_device_per_batch > 1 and not a.no_exposed_comm and a.mode != "no_sync":
+        pipe.set_mode("no_sync")
+        for _ in range(2):
+            image(False)
+        nosync_ms = timed(False, a.steps) / a.steps
+        pipe.set_mode(a.mode)
+        image(False)
+        exposed = {"ms_image_no_sync": nosync_ms, "exposed_comm_pct": 100.0 * (ms_image - nosync_ms) / ms_image,
+                   "definition": "(t(mode) - t(no_sync)) / t(mode) over the whole 50-step image (5 synchronous + 45 asynchronous steps)"}
+
     # ---- dominant-kernel roofline: one instrumented eager image, CUDA events around every fmha launch
     cfg.use_cuda_graph_saved = cfg.use_cuda_graph
     roof = None
@@ -256,7 +269,7 @@ def run_ours(a):
                 "config": {"workload": f"{a.model.upper()} UNet {R}x{R}, 50-step Euler, CFG batch 2, random-init weights",
                            "parallelism": f"cfg{2 if b == 1 else 1} x patch{n}", "mode": cfg.mode, "warmup_steps": cfg.warmup_steps,
                            "cuda_graph": cfg.use_cuda_graph, "l2": "working set (5.1 GB of weights per step) exceeds the 126 MB L2; no explicit flush"},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "exposed_comm": exposed,
                 "e2e": {"value": ms_image_e2e, "unit": "ms/image", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": launches, "clocks": clocks}
         print(json.dumps(line), flush=True)

@@ -7,12 +7,14 @@
 //     F.scaled_dot_product_attention -> S = Q K^T and O += P V as tcgen05.mma tiles, accumulators in TMEM
 // and the SDPA of DistriCrossAttentionPP.forward (attn.py:79-87) with nseg = 1, lseg = 77.
 //
-// CTA = one 128-row Q tile of one (batch, head).  192 threads:
+// CTA = one 128-row Q tile of one (batch, head).  192 threads, TWO CTAs per SM (256 TMEM columns and ~112 KB smem each) so
+// that two softmax warps share every SM sub-partition and hide each other's TMEM / barrier latencies:
 //   warps 0-3  softmax: thread i owns row i (= TMEM lane i): tcgen05.ld S, online softmax (exp2, lazy rescale),
 //              P written back to TMEM as fp16, O corrected in TMEM when the running max moved, epilogue O/l -> HBM
 //   warp 4     TMA producer: Q once, then K/V tiles through a 4-stage mbarrier ring; waits the peers' flags
-//   warp 5     MMA issuer (one lane): S[j&1] = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major)
-// TMEM columns: S0 [0,128) S1 [128,256) O [256,320) P [320,384)   (fp32 S/O, packed fp16 P)
+//   warp 5     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
+//              issued as soon as the softmax warps have pulled S_j into registers (s_free), i.e. under their exp work
+// TMEM columns: S [0,128) O [128,192) P [192,256)   (fp32 S/O, packed fp16 P)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,10 +26,10 @@ namespace {
 constexpr int BM = 128;      // Q rows per CTA
 constexpr int BN = 128;      // K/V rows per tile
 constexpr int HD = 64;       // padded head dim (d = 64, or d = 40 zero-filled by TMA)
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int NTHREADS = 192;
-constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_S0 = 0, COL_S1 = 128, COL_O = 256, COL_P = 320;
+constexpr uint32_t TMEM_COLS = 256;
+constexpr uint32_t COL_S = 0, COL_O = 128, COL_P = 192;
 constexpr uint32_t TILE_BYTES = BN * HD * 2;  // 16 KiB
 
 struct __align__(1024) Smem {
@@ -36,7 +38,8 @@ struct __align__(1024) Smem {
   __half v[STAGES][BN * HD];
   uint64_t q_full;
   uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
-  uint64_t s_full[2];
+  uint64_t s_full;
+  uint64_t s_free;
   uint64_t p_full;
   uint64_t pv_done;
   uint32_t tmem_base;
@@ -159,13 +162,14 @@ constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // B (=V) MN-major
 
 // ----------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(NTHREADS, 2)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
                 float scale_log2) {
-  extern __shared__ uint8_t smem_raw[];
-  Smem& sm = *reinterpret_cast<Smem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * BM, head = blockIdx.y, bat = blockIdx.z;
@@ -178,7 +182,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
       mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
     }
-    mbar_init(&sm.s_full[0], 1); mbar_init(&sm.s_full[1], 1);
+    mbar_init(&sm.s_full, 1);
+    mbar_init(&sm.s_free, 4);
     mbar_init(&sm.p_full, 4);
     mbar_init(&sm.pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -230,17 +235,20 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&sm.k_full[st], (uint32_t)(j / STAGES) & 1u);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sm.k[st]);
-        const uint32_t d_tmem = tmem + ((j & 1) ? COL_S1 : COL_S0);
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk)
-          mma_ss(d_tmem, smem_desc(q_addr + kk * 32, 16, 1024), smem_desc(k_addr + kk * 32, 16, 1024), IDESC_S, kk > 0);
+          mma_ss(tmem + COL_S, smem_desc(q_addr + kk * 32, 16, 1024), smem_desc(k_addr + kk * 32, 16, 1024), IDESC_S, kk > 0);
         tc_commit(&sm.k_empty[st]);
-        tc_commit(&sm.s_full[j & 1]);
+        tc_commit(&sm.s_full);
       };
       mbar_wait(&sm.q_full, 0);
       issue_qk(0);
       for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);
+        if (j + 1 < T) {
+          mbar_wait(&sm.s_free, (uint32_t)j & 1u);   // S_j is in the softmax warps' registers
+          tc_fence_after();
+          issue_qk(j + 1);
+        }
         const int st = j % STAGES;
         mbar_wait(&sm.p_full, (uint32_t)j & 1u);
         mbar_wait(&sm.v_full[st], (uint32_t)(j / STAGES) & 1u);
@@ -263,15 +271,18 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int j = 0; j < T; ++j) {
       const int t = j % tps;
       const int valid = min(BN, lseg - t * BN);
-      mbar_wait(&sm.s_full[j & 1], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&sm.s_full, (uint32_t)j & 1u);
       tc_fence_after();
       uint32_t sr[128];
-      const uint32_t s_addr = lane_base + ((j & 1) ? COL_S1 : COL_S0);
+      const uint32_t s_addr = lane_base + COL_S;
       tmem_ld32(s_addr + 0, sr + 0);
       tmem_ld32(s_addr + 32, sr + 32);
       tmem_ld32(s_addr + 64, sr + 64);
       tmem_ld32(s_addr + 96, sr + 96);
       tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
       if (valid < BN) {
 #pragma unroll
         for (int c = 0; c < BN; ++c)
@@ -428,7 +439,7 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   SegInfo segs;
   for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
   static bool attr_set = false;
-  const size_t smem_bytes = sizeof(Smem) + 1024;
+  const size_t smem_bytes = sizeof(Smem);
   if (!attr_set) {
     DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     attr_set = true;

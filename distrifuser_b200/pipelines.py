@@ -66,13 +66,21 @@ class _DistriPipelineBase:
             comm_manager.create_buffer()                             # pipelines.py:140-141
         unet.set_counter(0)
         unet(**static_inputs, return_dict=False, record=True)        # pre-run (pipelines.py:144-145)
+        self.static_inputs = static_inputs
+        self.comm_manager = comm_manager
+        self._capture_graphs()
+
+    @torch.no_grad()
+    def _capture_graphs(self):
+        """Three graphs: synchronous step, first asynchronous step, steady state (pipelines.py:147-165)."""
+        cfg, unet, static_inputs = self.distri_config, self.pipeline.unet, self.static_inputs
         static_outputs, cuda_graphs = [], []
-        if cfg.use_cuda_graph:                                       # pipelines.py:147-165
-            if comm_manager is not None:
-                comm_manager.clear()
+        unet.setup_cuda_graph(None, None, None)
+        if cfg.use_cuda_graph:
+            if self.comm_manager is not None:
+                self.comm_manager.clear()
             torch.cuda.synchronize()
             counters = [0, cfg.warmup_steps + 1, cfg.warmup_steps + 2]
-            # same static input tensors for every graph (the wrapper slices the CFG batch before recording)
             unet.static_inputs = None
             pool = None
             from . import _lib
@@ -88,8 +96,12 @@ class _DistriPipelineBase:
                 pool = graph.pool()
                 cuda_graphs.append(graph)
             unet.setup_cuda_graph(static_outputs, cuda_graphs, launches)
-        self.static_inputs = static_inputs
-        self.comm_manager = comm_manager
+
+    def set_mode(self, mode: str):
+        """Switch the synchronisation mode (e.g. to "no_sync", the compute-only lower bound used for the exposed
+        communication metric) on the same arena and re-capture the graphs."""
+        self.distri_config.mode = mode
+        self._capture_graphs()
 
 
 class DistriSDXLPipeline(_DistriPipelineBase):

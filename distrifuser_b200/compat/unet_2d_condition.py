@@ -67,7 +67,11 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
+        y = self.proj(x)
+        if y.is_cuda and y.dtype == torch.float16:
+            from ..ops import geglu
+            return geglu(y)                      # one fused kernel instead of gelu + mul
+        x, gate = y.chunk(2, dim=-1)
         return x * F.gelu(gate)
 
 
@@ -152,10 +156,11 @@ class ResnetBlock2D(nn.Module):
         if not self.fused_norm_act:
             h = self.nonlinearity(h)
         h = self.conv1(h)
-        h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
-        h = self.norm2(h)
-        if not self.fused_norm_act:
-            h = self.nonlinearity(h)
+        t = self.time_emb_proj(self.nonlinearity(temb))
+        if self.fused_norm_act:
+            h = self.norm2(h, addend=t)          # GroupNorm(h + t[:, :, None, None]) + SiLU in one kernel pair
+        else:
+            h = self.nonlinearity(self.norm2(h + t[:, :, None, None]))
         h = self.conv2(h)
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)

@@ -7,12 +7,14 @@
 //     F.scaled_dot_product_attention -> S = Q K^T and O += P V as tcgen05.mma tiles, accumulators in TMEM
 // and the SDPA of DistriCrossAttentionPP.forward (attn.py:79-87) with nseg = 1, lseg = 77.
 //
-// CTA = one 128-row Q tile of one (batch, head).  192 threads, TWO CTAs per SM (256 TMEM columns and ~112 KB smem each) so
-// that two softmax warps share every SM sub-partition and hide each other's TMEM / barrier latencies:
-//   warps 0-3  softmax: thread i owns row i (= TMEM lane i): tcgen05.ld S, online softmax (exp2, lazy rescale),
-//              P written back to TMEM as fp16, O corrected in TMEM when the running max moved, epilogue O/l -> HBM
-//   warp 4     TMA producer: Q once, then K/V tiles through a 4-stage mbarrier ring; waits the peers' flags
-//   warp 5     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
+// CTA = one 128-row Q tile of one (batch, head).  320 threads, TWO CTAs per SM (256 TMEM columns, ~97 KB smem each):
+//   warps 0-7  softmax: every S row is shared by two threads (warp q handles columns [0,64) of rows 32q.., warp q+4 the
+//              columns [64,128) of the same rows), so 4 softmax warps live on every SM sub-partition (2 CTAs x 2) and hide
+//              each other's fixed-latency stalls -- with one thread per row the kernel sat at 54 % issue utilisation with
+//              "wait" as the top stall (profiles/r1_fmha_v1c_3840.txt).  tcgen05.ld S, partial max exchanged through smem,
+//              exp2 (packed FFMA2/FADD2, part polynomial), P back to TMEM as fp16, lazy O correction, epilogue O/l -> HBM
+//   warp 8     TMA producer: Q once, then K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
+//   warp 9     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
 //              issued as soon as the softmax warps have pulled S_j into registers (s_free), i.e. under their exp work
 // TMEM columns: S [0,128) O [128,192) P [192,256)   (fp32 S/O, packed fp16 P)
 #include <cuda.h>
@@ -26,18 +28,22 @@ namespace {
 constexpr int BM = 128;      // Q rows per CTA
 constexpr int BN = 128;      // K/V rows per tile
 constexpr int HD = 64;       // padded head dim (d = 64, or d = 40 zero-filled by TMA)
-constexpr int STAGES = 3;
-constexpr int NTHREADS = 192;
+constexpr int KSTAGES = 3, VSTAGES = 2;
+constexpr int NSOFTMAX_WARPS = 8;
+constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + 2);
+constexpr int WARP_TMA = NSOFTMAX_WARPS, WARP_MMA = NSOFTMAX_WARPS + 1;
 constexpr uint32_t TMEM_COLS = 256;
 constexpr uint32_t COL_S = 0, COL_O = 128, COL_P = 192;
 constexpr uint32_t TILE_BYTES = BN * HD * 2;  // 16 KiB
 
 struct __align__(1024) Smem {
   __half q[BM * HD];
-  __half k[STAGES][BN * HD];
-  __half v[STAGES][BN * HD];
+  __half k[KSTAGES][BN * HD];
+  __half v[VSTAGES][BN * HD];
+  float red_max[2][2][BM];   // [tile parity][column half][row]: partial row maxima exchanged between the two half-row warps
+  float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue
   uint64_t q_full;
-  uint64_t k_full[STAGES], k_empty[STAGES], v_full[STAGES], v_empty[STAGES];
+  uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
   uint64_t s_full;
   uint64_t s_free;
   uint64_t p_full;
@@ -72,17 +78,25 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
   const uint64_t t0 = globaltimer_ns();
-  uint32_t polls = 0;
-  while (!mbar_try(bar, parity)) {
-    if ((++polls & 4095u) == 0 && globaltimer_ns() - t0 > 10000000000ull) {
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 4096; ++i)
+      if (mbar_try(bar, parity)) return;
+    if (globaltimer_ns() - t0 > 10000000000ull) {      // a broken pipeline becomes a CUDA error instead of a hung GPU
       printf("distrifuser_b200 fmha: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  // try_wait suspends the thread for a hardware time slice, so this loop is two instructions per poll
+#pragma unroll 1
+  for (int i = 0; i < 64; ++i)
+    if (mbar_try(bar, parity)) return;
+  mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -152,6 +166,62 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2: two elements per issue slot) and 3-input max
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x for a pair, entirely on the FMA/ALU pipes (the MUFU pipe is the bottleneck of d=64 attention): Cody-Waite split
+// x = n + f by adding 1.5*2^23 with round-to-minus-infinity, degree-3 minimax polynomial for 2^f on [0,1) (rel. err < 1e-4,
+// below the fp16 rounding of P), then n is added straight into the exponent field.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+  const uint64_t magic = pack2(12582912.f, 12582912.f);
+  const uint64_t r2 = add2_rm(x2, magic);
+  const uint64_t f2 = sub2(x2, sub2(r2, magic));
+  uint64_t q2 = fma2(f2, pack2(0.077119089663028717041015625f, 0.077119089663028717041015625f),
+                     pack2(0.227564394474029541015625f, 0.227564394474029541015625f));
+  q2 = fma2(q2, f2, pack2(0.695146143436431884765625f, 0.695146143436431884765625f));
+  q2 = fma2(q2, f2, pack2(1.f, 1.f));
+  float r0, r1, q0, q1;
+  unpack2(r2, r0, r1);
+  unpack2(q2, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
+}
+#ifndef DF_EMU_PAIRS_OF_8
+#define DF_EMU_PAIRS_OF_8 2   // of every 8 element pairs, this many take the polynomial path
+#endif
+
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -176,19 +246,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int tps = (lseg + BN - 1) / BN;  // tiles per segment
   const int T = nseg * tps;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == WARP_MMA && lane == 0) {
     mbar_init(&sm.q_full, 1);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1);
-      mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1);
-    }
+    for (int s = 0; s < KSTAGES; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1); }
+    for (int s = 0; s < VSTAGES; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1); }
     mbar_init(&sm.s_full, 1);
-    mbar_init(&sm.s_free, 4);
-    mbar_init(&sm.p_full, 4);
+    mbar_init(&sm.s_free, NSOFTMAX_WARPS);
+    mbar_init(&sm.p_full, NSOFTMAX_WARPS);
     mbar_init(&sm.pv_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -197,7 +265,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     // =============================================================== TMA producer
     if (lane == 0) {
       prefetch_tmap(&tm_q);
@@ -206,8 +274,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tma_load_4d(sm.q, &tm_q, &sm.q_full, 0, head, q0, bat);
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
-      for (int j = 0; j < T; ++j) {
-        const int so = j / tps, t = j - so * tps;
+      int so = 0, t = 0;                       // segment order index, tile inside the segment (no divisions in the loop)
+      for (int j = 0; j < T; ++j, ++t) {
+        if (t == tps) { t = 0; ++so; }
         int seg = own_seg + so;
         if (seg >= nseg) seg -= nseg;
         const void* map = &tm_kv_own;
@@ -216,23 +285,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           if (t == 0 && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
           map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
         }
-        const int st = j % STAGES;
-        const uint32_t ph = (uint32_t)(j / STAGES) & 1u;
-        mbar_wait(&sm.k_empty[st], ph ^ 1u);
-        mbar_expect_tx(&sm.k_full[st], TILE_BYTES);
-        tma_load_4d(sm.k[st], map, &sm.k_full[st], 0, head, t * BN, bat);
-        mbar_wait(&sm.v_empty[st], ph ^ 1u);
-        mbar_expect_tx(&sm.v_full[st], TILE_BYTES);
-        tma_load_4d(sm.v[st], map, &sm.v_full[st], 0, heads + head, t * BN, bat);
+        const int ks = j % KSTAGES, vs = j % VSTAGES;
+        mbar_wait(&sm.k_empty[ks], ((uint32_t)(j / KSTAGES) & 1u) ^ 1u);
+        mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
+        tma_load_4d(sm.k[ks], map, &sm.k_full[ks], 0, head, t * BN, bat);
+        mbar_wait(&sm.v_empty[vs], ((uint32_t)(j / VSTAGES) & 1u) ^ 1u);
+        mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
+        tma_load_4d(sm.v[vs], map, &sm.v_full[vs], 0, heads + head, t * BN, bat);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == WARP_MMA) {
     // =============================================================== MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t q_addr = smem_u32(sm.q);
       auto issue_qk = [&](int j) {
-        const int st = j % STAGES;
-        mbar_wait(&sm.k_full[st], (uint32_t)(j / STAGES) & 1u);
+        const int st = j % KSTAGES;
+        mbar_wait(&sm.k_full[st], (uint32_t)(j / KSTAGES) & 1u);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sm.k[st]);
 #pragma unroll
@@ -249,9 +317,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tc_fence_after();
           issue_qk(j + 1);
         }
-        const int st = j % STAGES;
+        const int st = j % VSTAGES;
         mbar_wait(&sm.p_full, (uint32_t)j & 1u);
-        mbar_wait(&sm.v_full[st], (uint32_t)(j / STAGES) & 1u);
+        mbar_wait(&sm.v_full[st], (uint32_t)(j / VSTAGES) & 1u);
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sm.v[st]);
 #pragma unroll
@@ -263,40 +331,44 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
   } else {
-    // =============================================================== softmax / correction / epilogue (warps 0-3)
-    const int row = threadIdx.x;                                   // == TMEM lane
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    // =============================================================== softmax / correction / epilogue (warps 0-7)
+    const int quad = warp & 3, half = warp >> 2;                   // TMEM lane quarter, S column half
+    const int row = quad * 32 + lane;                              // == TMEM lane
+    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const uint32_t pair_bar = 1 + quad;                            // named barrier shared by warps `quad` and `quad + 4`
+    constexpr int HN = BN / 2;                                     // S columns per thread
     float m_ref = -INFINITY;                                       // max used as exponent reference (raw S units)
-    float l = 0.f;
-    for (int j = 0; j < T; ++j) {
-      const int t = j % tps;
-      const int valid = min(BN, lseg - t * BN);
+    float l = 0.f;                                                 // partial row sum over this thread's columns
+    int t = 0;                                                     // tile inside the current segment
+    for (int j = 0; j < T; ++j, ++t) {
+      if (t == tps) t = 0;
+      const int valid = min(BN, lseg - t * BN) - half * HN;        // valid columns inside this thread's half
       mbar_wait(&sm.s_full, (uint32_t)j & 1u);
       tc_fence_after();
-      uint32_t sr[128];
-      const uint32_t s_addr = lane_base + COL_S;
+      uint32_t sr[HN];
+      const uint32_t s_addr = lane_base + COL_S + half * HN;
       tmem_ld32(s_addr + 0, sr + 0);
       tmem_ld32(s_addr + 32, sr + 32);
-      tmem_ld32(s_addr + 64, sr + 64);
-      tmem_ld32(s_addr + 96, sr + 96);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
-      if (valid < BN) {
+      if (valid < HN) {                          // ragged last tile of a segment only
+        asm volatile("" ::: "memory");            // keep this a real (warp-uniform) branch: if-converted it costs 2 instr / element on every tile
 #pragma unroll
-        for (int c = 0; c < BN; ++c)
+        for (int c = 0; c < HN; ++c)
           if (c >= valid) sr[c] = 0xff800000u;  // -inf
       }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < BN; c += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[c]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[c + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sr[c + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sr[c + 3]));
+      for (int c = 0; c < HN; c += 4) {
+        mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+        mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
       }
-      const float m_new = fmaxf(fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)), m_ref);
+      const float pm = fmaxf(mx0, mx1);
+      sm.red_max[j & 1][half][row] = pm;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float m_new = max3(pm, sm.red_max[j & 1][half ^ 1][row], m_ref);
       // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
       float alpha = 1.f;
       bool moved = false;
@@ -307,50 +379,59 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         moved = true;
       }
       const float neg_ref = -m_ref * scale_log2;
-      uint32_t pr[64];
-      float sum0 = 0.f, sum1 = 0.f;
+      const uint64_t scale2 = pack2(scale_log2, scale_log2), negref2 = pack2(neg_ref, neg_ref);
+      uint32_t pr[HN / 2];
+      uint64_t sum2 = pack2(0.f, 0.f);
 #pragma unroll
-      for (int c = 0; c < BN; c += 2) {
-        float p0 = ex2(fmaf(__uint_as_float(sr[c]), scale_log2, neg_ref));
-        float p1 = ex2(fmaf(__uint_as_float(sr[c + 1]), scale_log2, neg_ref));
-        sum0 += p0; sum1 += p1;
-        pr[c >> 1] = pack_h2(p0, p1);
+      for (int pi = 0; pi < HN / 2; ++pi) {
+        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), scale2, negref2);
+        float p0, p1;
+        if ((pi & 7) < DF_EMU_PAIRS_OF_8) {
+          ex2_poly2(x2, p0, p1);
+        } else {
+          float x0, x1;
+          unpack2(x2, x0, x1);
+          p0 = ex2(x0);
+          p1 = ex2(x1);
+        }
+        sum2 = add2(sum2, pack2(p0, p1));
+        pr[pi] = pack_h2(p0, p1);
       }
+      float sum0, sum1;
+      unpack2(sum2, sum0, sum1);
       l += sum0 + sum1;
       if (j > 0) {
         mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
         tc_fence_after();
-        if (__any_sync(0xffffffffu, moved)) {
-          uint32_t o[64];
-          tmem_ld32(lane_base + COL_O, o);
-          tmem_ld32(lane_base + COL_O + 32, o + 32);
+        if (__any_sync(0xffffffffu, moved)) {            // this warp owns O columns [32*half, 32*half + 32)
+          uint32_t o[32];
+          tmem_ld32(lane_base + COL_O + half * 32, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 64; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st32(lane_base + COL_O, o);
-          tmem_st32(lane_base + COL_O + 32, o + 32);
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+          tmem_st32(lane_base + COL_O + half * 32, o);
         }
       }
-      tmem_st32(lane_base + COL_P, pr);
-      tmem_st32(lane_base + COL_P + 32, pr + 32);
+      tmem_st32(lane_base + COL_P + half * (HN / 2), pr);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full);
     }
-    // ---- epilogue: O / l -> fp16 -> HBM
+    // ---- epilogue: O / l -> fp16 -> HBM (each half-row warp writes its 32 columns)
+    sm.red_sum[half][row] = l;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float inv_l = 1.f / (sm.red_sum[0][row] + sm.red_sum[1][row]);
     mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
     tc_fence_after();
-    uint32_t o[64];
-    tmem_ld32(lane_base + COL_O, o);
-    tmem_ld32(lane_base + COL_O + 32, o + 32);
+    uint32_t o[32];
+    tmem_ld32(lane_base + COL_O + half * 32, o);
     tmem_wait_ld();
-    const float inv_l = 1.f / l;
     if (q0 + row < lq) {
-      __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d;
-      const int nvec = d / 8;
+      __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + half * 32;
+      const int nvec = (d - half * 32) / 8;       // 16-byte vectors of real (un-padded) head columns in this half
 #pragma unroll
-      for (int vq = 0; vq < HD / 8; ++vq) {
+      for (int vq = 0; vq < 4; ++vq) {
         if (vq < nvec) {
           int4 w;
           w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
@@ -364,7 +445,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == WARP_TMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
   }
 }

@@ -1,10 +1,11 @@
 // distrifuser_b200 -- GroupNorm with cross-rank sufficient statistics (NHWC fp16).
 // Replaces DistriGroupNorm.forward (distrifuser/modules/pp/groupnorm.py:14-97): the ~10 eager reduction /
 // elementwise kernels and the 256-byte NCCL all_gather / all_reduce per layer become
-//   (1) gn_stats_kernel    one HBM read, fp32 per-channel register accumulation, per-CTA partial moments
-//   (2) gn_exchange_kernel one CTA: reduces the partials, exchanges (E[x], E[x^2]) with the patch group through
-//                          peer stores + release/acquire flags over NVLink, applies the mode formula
-//   (3) gn_apply_kernel    one read (L2-resident for <= ~60 MB activations) + one write, optional fused SiLU
+//   (1) gn_stats_kernel    one HBM read, fp32 per-channel register accumulation, per-CTA partial moments; the LAST CTA to
+//                          finish reduces the partials, exchanges (E[x], E[x^2]) with the patch group through peer stores +
+//                          release/acquire flags over NVLink and applies the mode formula (gn_exchange)
+//   (2) gn_apply_kernel    one read (L2-resident for <= ~60 MB activations) + one write, optional fused SiLU
+// Both accept a per-(sample, channel) addend so that ResnetBlock2D's `conv1(x) + time_emb` never materialises.
 #include "common.cuh"
 
 using namespace df;
@@ -46,9 +47,23 @@ __device__ __forceinline__ void unpack8(const int4& v, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, float2* __restrict__ partial, int hw,
-                                                       int C, int G, int V, int lanes, int ppc) {
-  extern __shared__ float acc[];  // [G][2]
+struct GnExchange {   // everything the last CTA needs to finish the statistics (was a separate 1-CTA kernel: 23 us of latency)
+  df_comm_t c;
+  float2* coef;
+  unsigned int* ticket;
+  int bG, nchunk_total;
+  float inv_ne, bessel, eps;
+  int mode, neg_fb, idx;
+  uint64_t tensor_off, slot_bytes;
+  uint32_t group_mask;
+};
+
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine);
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                                       float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
+                                                       int ppc, GnExchange ex) {
+  extern __shared__ float acc[];  // [G][2], reused as float2 mine[bG] by the last CTA
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * G; i += blockDim.x) acc[i] = 0.f;
@@ -57,9 +72,10 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
   if (pl < lanes) {
     const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
     const __half* base = x + ((size_t)b * hw) * C + (size_t)v * 8;
-    float s[8], ss[8];
+    float s[8], ss[8], ad[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = ss[j] = 0.f;
+    for (int j = 0; j < 8; ++j) s[j] = ss[j] = ad[j] = 0.f;
+    if (addend) unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);   // per-(sample, channel) bias, e.g. the time embedding
     int p = p0 + pl;
     for (; p + 3 * lanes < p1; p += 4 * lanes) {
       int4 r[4];
@@ -70,14 +86,14 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
         float f[8];
         unpack8(r[u], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+        for (int j = 0; j < 8; ++j) { float t = f[j] + ad[j]; s[j] += t; ss[j] = fmaf(t, t, ss[j]); }
       }
     }
     for (; p < p1; p += lanes) {
       float f[8];
       unpack8(ld_nc_v4(base + (size_t)p * C), f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { s[j] += f[j]; ss[j] = fmaf(f[j], f[j], ss[j]); }
+      for (int j = 0; j < 8; ++j) { float t = f[j] + ad[j]; s[j] += t; ss[j] = fmaf(t, t, ss[j]); }
     }
     // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
     const int cpg = C / G;
@@ -99,23 +115,47 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
   __syncthreads();
   for (int g = tid; g < G; g += blockDim.x)
     partial[((size_t)b * nchunk + chunk) * G + g] = make_float2(acc[2 * g], acc[2 * g + 1]);
+  // last CTA of the grid finishes the job: reduce the partials, exchange with the patch group, write (mean, rstd)
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    unsigned int t = atomicAdd(ex.ticket, 1u);
+    is_last = (t == (unsigned int)ex.nchunk_total - 1);
+    if (is_last) *ex.ticket = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  gn_exchange(ex, partial, G, nchunk, reinterpret_cast<float2*>(acc));
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
-__global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const float2* __restrict__ partial,
-                                                          float2* __restrict__ coef, int bG, int G, int nchunk,
-                                                          float inv_ne, float bessel, float eps, int mode, int neg_fb,
-                                                          int idx, uint64_t tensor_off, uint64_t slot_bytes,
-                                                          uint32_t group_mask) {
-  extern __shared__ float2 mine[];  // [bG]
-  const int tid = threadIdx.x;
-  for (int i = tid; i < bG; i += blockDim.x) {
-    int b = i / G, g = i - b * G;
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine) {
+  const df_comm_t& c = e.c;
+  float2* __restrict__ coef = e.coef;
+  const int bG = e.bG, mode = e.mode, neg_fb = e.neg_fb, idx = e.idx;
+  const float inv_ne = e.inv_ne, bessel = e.bessel, eps = e.eps;
+  const uint64_t tensor_off = e.tensor_off, slot_bytes = e.slot_bytes;
+  const uint32_t group_mask = e.group_mask;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  // parallel reduction of the per-CTA partials: `tpp` threads per (sample, group) pair, then a shared-memory fold
+  __shared__ float2 red[512];
+  const int tpp = max(1, min(nthr / bG, 8));
+  if (tid < bG * tpp) {
+    const int i = tid / tpp, r = tid - i * tpp;
+    const int b = i / G, g = i - b * G;
     float s = 0.f, ss = 0.f;
-    for (int k = 0; k < nchunk; ++k) {
+    for (int k = r; k < nchunk; k += tpp) {
       float2 p = partial[((size_t)b * nchunk + k) * G + g];
       s += p.x; ss += p.y;
     }
+    red[tid] = make_float2(s, ss);
+  }
+  __syncthreads();
+  for (int i = tid; i < bG; i += nthr) {
+    float s = 0.f, ss = 0.f;
+    for (int r = 0; r < tpp; ++r) { s += red[i * tpp + r].x; ss += red[i * tpp + r].y; }
     mine[i] = make_float2(s * inv_ne, ss * inv_ne);
   }
   __syncthreads();
@@ -128,7 +168,7 @@ __global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const flo
     for (int p = 0; p < c.world; ++p) {
       if (!(group_mask >> p & 1)) continue;
       float2* dst = (float2*)slot_ptr(c, p, pub, tensor_off, slot_bytes, c.rank);
-      for (int i = tid; i < bG; i += blockDim.x) dst[i] = mine[i];
+      for (int i = tid; i < bG; i += nthr) dst[i] = mine[i];
     }
     __threadfence_system();
     __syncthreads();
@@ -142,7 +182,7 @@ __global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const flo
   if (mode == 1) publish();          // fresh statistics are needed by everyone in this very step
   if (mode != 0) wait_all();         // sync: this epoch's; async: the previous epoch's (1-step stale)
 
-  for (int i = tid; i < bG; i += blockDim.x) {
+  for (int i = tid; i < bG; i += nthr) {
     float2 m = mine[i];
     float mean = m.x, msq = m.y;
     if (mode != 0) {
@@ -167,8 +207,9 @@ __global__ void __launch_bounds__(256) gn_exchange_kernel(df_comm_t c, const flo
   if (mode >= 2) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
 }
 
-__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
-                                                       const __half* __restrict__ gamma, const __half* __restrict__ beta,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                                       __half* __restrict__ y, const __half* __restrict__ gamma,
+                                                       const __half* __restrict__ beta,
                                                        const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
                                                        int ppc, int silu) {
   const int b = blockIdx.y, chunk = blockIdx.x;
@@ -184,6 +225,12 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
     float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
     sc[j] = mr.y * ga;
     sh[j] = be - mr.x * sc[j];
+  }
+  if (addend) {                     // y = ((x + a) - mean) * rstd * gamma + beta  ==  x * sc + (sh + a * sc)
+    float ad[8];
+    unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[j] = fmaf(ad[j], sc[j], sh[j]);
   }
   const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
   const size_t base = ((size_t)b * hw) * C + (size_t)v * 8;
@@ -220,32 +267,38 @@ extern "C" size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, in
   return ((size_t)b * p.nchunk * groups + (size_t)b * groups) * sizeof(float2) + 256;
 }
 
-extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, void* y, const void* gamma, const void* beta, int b,
-                                int h, int w, int C, int groups, float eps, int mode, int bessel, int neg_var_fallback,
-                                int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes, uint32_t group_mask,
-                                void* scratch, void* stream) {
+extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
+                                const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
+                                int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
+                                uint32_t group_mask, void* scratch, void* stream) {
   DF_REQUIRE(C % 8 == 0 && C % groups == 0 && C / 8 <= 512, "df_groupnorm_fwd: unsupported channel count %d", C);
-  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0, "df_groupnorm_fwd: x/y must be 16-byte aligned");
+  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)addend % 16) == 0,
+             "df_groupnorm_fwd: x / y / addend must be 16-byte aligned");
   DF_REQUIRE(mode >= 0 && mode <= 3, "df_groupnorm_fwd: bad mode %d", mode);
+  DF_REQUIRE(b * groups <= 512 && groups <= 256, "df_groupnorm_fwd: b*groups = %d exceeds the exchange buffer", b * groups);
   DF_REQUIRE(mode == 0 || (slot_bytes >= (uint64_t)b * groups * 8 && (group_mask >> comm.rank & 1)),
              "df_groupnorm_fwd: statistics slot too small or rank outside its own group");
   cudaStream_t st = (cudaStream_t)stream;
   GnPlan p = gn_plan(b, h, w, C);
-  float2* partial = (float2*)scratch;
+  // scratch: [ticket (256 B, zero-initialised by the caller once)] [partials] [coef]
+  unsigned int* ticket = (unsigned int*)scratch;
+  float2* partial = (float2*)((char*)scratch + 256);
   float2* coef = partial + (size_t)b * p.nchunk * groups;
   const int hw = h * w;
   const long long ne = (long long)(C / groups) * hw;
-  gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, 2 * groups * sizeof(float), st>>>((const __half*)x, partial, hw, C,
-                                                                                   groups, p.V, p.lanes, p.ppc);
+  GnExchange ex;
+  ex.c = comm; ex.coef = coef; ex.ticket = ticket; ex.bG = b * groups; ex.nchunk_total = p.nchunk * b;
+  ex.inv_ne = (float)(1.0 / (double)ne);
+  ex.bessel = bessel ? (float)((double)ne / (double)(ne - 1)) : 1.f;
+  ex.eps = eps; ex.mode = mode; ex.neg_fb = neg_var_fallback; ex.idx = idx;
+  ex.tensor_off = tensor_off; ex.slot_bytes = slot_bytes; ex.group_mask = group_mask;
+  size_t smem = (size_t)(2 * groups > 2 * b * groups ? 2 * groups : 2 * b * groups) * sizeof(float);
+  gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, partial, hw, C, groups,
+                                                             p.V, p.lanes, p.ppc, ex);
   DF_CHECK_LAUNCH();
-  float bess = bessel ? (float)((double)ne / (double)(ne - 1)) : 1.f;
-  gn_exchange_kernel<<<1, 256, (size_t)b * groups * sizeof(float2), st>>>(
-      comm, partial, coef, b * groups, groups, p.nchunk, (float)(1.0 / (double)ne), bess, eps, mode, neg_var_fallback, idx,
-      tensor_off, slot_bytes, group_mask);
-  DF_CHECK_LAUNCH();
-  gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (__half*)y, (const __half*)gamma,
-                                                           (const __half*)beta, coef, hw, C, groups, p.V, p.lanes, p.ppc,
-                                                           fuse_silu);
+  gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (const __half*)addend, (__half*)y,
+                                                           (const __half*)gamma, (const __half*)beta, coef, hw, C, groups, p.V,
+                                                           p.lanes, p.ppc, fuse_silu);
   DF_CHECK_LAUNCH();
   return 0;
 }

@@ -38,7 +38,8 @@ class DistriGroupNorm(BaseModule):
             return (MODE_SYNC if self._bound() else MODE_LOCAL), 1, 0      # groupnorm.py:74-91
         return MODE_LOCAL, 0, 0                                      # groupnorm.py:92-93 (stock nn.GroupNorm)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, addend: torch.Tensor | None = None) -> torch.Tensor:
+        """`addend` ([b, C], optional) is added to every pixel before the norm: GroupNorm(x + addend[:, :, None, None])."""
         module = self.module
         cfg = self.distri_config
         assert x.ndim == 4
@@ -55,7 +56,7 @@ class DistriGroupNorm(BaseModule):
         L = _lib.lib()
         nbytes = L.df_groupnorm_scratch_bytes(b, G, h, w, c)
         if self._scratch is None or self._scratch.numel() < nbytes:
-            self._scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            self._scratch = torch.zeros(nbytes, dtype=torch.uint8, device=x.device)   # carries a self-resetting ticket
         cm = self.comm_manager
         if mode != MODE_LOCAL:
             comm, off, sb, mask = cm.group, cm.tensor_off[self.idx], cm.slot_bytes[self.idx], cm.group_mask()
@@ -67,7 +68,10 @@ class DistriGroupNorm(BaseModule):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
+        if addend is not None:
+            addend = addend.reshape(b, c).contiguous()
+            assert addend.dtype == x.dtype
+        _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
                                       mode, bessel, neg_fb, int(self.fuse_silu), self.idx or 0, off, sb, mask,
                                       self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
                    "df_groupnorm_fwd")

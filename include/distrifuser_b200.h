@@ -86,10 +86,13 @@ int df_slot_wait(df_comm_t comm, int idx, uint32_t src_mask, void* stream);
  *            3 stale_gn               (groupnorm.py:52-55)
  *      bessel != 0 multiplies the variance by ne/(ne-1) with the LOCAL element count (groupnorm.py:65-66);
  *      neg_var_fallback != 0 replaces negative variance by the local variance (groupnorm.py:60-63).
- *      group_mask selects the patch group (world ranks sharing this CFG branch); stats slots hold
- *      2*b*G fp32 (mean, mean of squares).  `scratch` >= df_groupnorm_scratch_bytes(). -------------- */
+ *      group_mask selects the patch-group members (bit i = group rank i); stats slots hold 2*b*G fp32
+ *      (mean, mean of squares).  `scratch` >= df_groupnorm_scratch_bytes(). ---------------------------- */
 size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, int C);
-int df_groupnorm_fwd(df_comm_t comm, const void* x, void* y, const void* gamma, const void* beta,
+/* `addend` (nullable): [b, C] fp16 added to every pixel before the statistics and the normalisation, i.e. the
+ * kernel computes GroupNorm(x + addend[:, :, None, None]) -- ResnetBlock2D's time-embedding add, fused.
+ * `scratch` must be zero-filled once when it is allocated (it carries a self-resetting CTA ticket). */
+int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma, const void* beta,
                      int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
                      int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                      uint32_t group_mask, void* scratch, void* stream);
@@ -129,6 +132,11 @@ int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, co
  *      all `world` flags and copies the assembled image to `out`. ---------------------------------- */
 int df_output_gather(df_comm_t comm, const void* strip, void* out, int B, int C, int H, int W, int bs, int hs,
                      int batch0, int row0, int idx, uint64_t tensor_off, void* stream);
+
+/* ---- fused GEGLU gate of the transformer feed-forward: out[r, c] = in[r, c] * gelu_erf(in[r, cols + c]).
+ *      Not one of the reference's wrapped modules (diffusers FeedForward) but on the per-step
+ *      path inside DistriUNetPP.forward; in:[rows, 2*cols] fp16 (pitch in_pitch elements), out:[rows, cols]. ---- */
+int df_geglu(const void* in, void* out, int64_t rows, int cols, int64_t in_pitch, int64_t out_pitch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,19 +27,19 @@ namespace {
 
 constexpr int BM = 128;      // Q rows per CTA
 constexpr int BN = 128;      // K/V rows per tile
-constexpr int HD = 64;       // padded head dim (d = 64, or d = 40 zero-filled by TMA)
-constexpr int KSTAGES = 3, VSTAGES = 2;
+constexpr int HB = 64;       // head-dim block: one 128-byte swizzled row; d is padded to NBLK * 64 columns (TMA zero-fills)
 constexpr int NSOFTMAX_WARPS = 8;
 constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + 2);
 constexpr int WARP_TMA = NSOFTMAX_WARPS, WARP_MMA = NSOFTMAX_WARPS + 1;
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t COL_S = 0, COL_O = 128, COL_P = 192;
-constexpr uint32_t TILE_BYTES = BN * HD * 2;  // 16 KiB
+constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;   // S fp32 [0,128), P packed fp16 [128,192), O fp32 [192, 192 + 64*NBLK)
+constexpr uint32_t BLK_BYTES = BN * HB * 2;                // one 128 x 64 fp16 block = 16 KiB
 
-struct __align__(1024) Smem {
-  __half q[BM * HD];
-  __half k[KSTAGES][BN * HD];
-  __half v[VSTAGES][BN * HD];
+// NBLK = ceil(d / 64): 1 for d in {40, 64} (SDXL, SD1.x level 0: two CTAs per SM), 2 for d = 80, 3 for d = 160 (SD1.x)
+template <int NBLK, int KSTAGES, int VSTAGES>
+struct __align__(1024) SmemT {
+  __half q[NBLK][BM * HB];
+  __half k[KSTAGES][NBLK][BN * HB];
+  __half v[VSTAGES][NBLK][BN * HB];
   float red_max[2][2][BM];   // [tile parity][column half][row]: partial row maxima exchanged between the two half-row warps
   float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue
   uint64_t q_full;
@@ -50,6 +50,10 @@ struct __align__(1024) Smem {
   uint64_t pv_done;
   uint32_t tmem_base;
 };
+template <int NBLK> struct Cfg;
+template <> struct Cfg<1> { static constexpr int KST = 3, VST = 2, CTAS = 2; static constexpr uint32_t TMEM = 256; };
+template <> struct Cfg<2> { static constexpr int KST = 2, VST = 2, CTAS = 1; static constexpr uint32_t TMEM = 512; };
+template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 
 struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
@@ -67,14 +71,17 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef DF_TRYWAIT_HINT_NS
+#define DF_TRYWAIT_HINT_NS 200000u
+#endif
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): sleep in hardware,
+      "selp.u32 %0, 1, 0, p;\n\t}"                                        // polling steals issue slots from the softmax warps
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(DF_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -91,10 +98,13 @@ __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+#ifndef DF_SPIN_FAST_POLLS
+#define DF_SPIN_FAST_POLLS 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   // try_wait suspends the thread for a hardware time slice, so this loop is two instructions per poll
 #pragma unroll 1
-  for (int i = 0; i < 64; ++i)
+  for (int i = 0; i < DF_SPIN_FAST_POLLS; ++i)
     if (mbar_try(bar, parity)) return;
   mbar_wait_slow(bar, parity);
 }
@@ -229,14 +239,18 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 
 // instruction descriptors (kind::f16, fp16 inputs, fp32 accumulate, M = 128)
 constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);               // K-major A, K-major B
-constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 16) | ((uint32_t)(HD >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // B (=V) MN-major
+constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 16) | ((uint32_t)(HB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // B (=V) MN-major, N = 64
 
 // ----------------------------------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(NTHREADS, 2)
+template <int NBLK>
+__global__ void __launch_bounds__(NTHREADS, Cfg<NBLK>::CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
                 float scale_log2) {
+  constexpr int KSTAGES = Cfg<NBLK>::KST, VSTAGES = Cfg<NBLK>::VST;
+  constexpr uint32_t TMEM_COLS = Cfg<NBLK>::TMEM, TILE_BYTES = NBLK * BLK_BYTES;
+  using Smem = SmemT<NBLK, KSTAGES, VSTAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
@@ -270,8 +284,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       prefetch_tmap(&tm_q);
       prefetch_tmap(&tm_kv_own);
-      mbar_expect_tx(&sm.q_full, BM * HD * 2);
-      tma_load_4d(sm.q, &tm_q, &sm.q_full, 0, head, q0, bat);
+      mbar_expect_tx(&sm.q_full, TILE_BYTES);
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
       int so = 0, t = 0;                       // segment order index, tile inside the segment (no divisions in the loop)
@@ -288,10 +303,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int ks = j % KSTAGES, vs = j % VSTAGES;
         mbar_wait(&sm.k_empty[ks], ((uint32_t)(j / KSTAGES) & 1u) ^ 1u);
         mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
-        tma_load_4d(sm.k[ks], map, &sm.k_full[ks], 0, head, t * BN, bat);
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.k[ks][blk], map, &sm.k_full[ks], blk * HB, head, t * BN, bat);
         mbar_wait(&sm.v_empty[vs], ((uint32_t)(j / VSTAGES) & 1u) ^ 1u);
         mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
-        tma_load_4d(sm.v[vs], map, &sm.v_full[vs], 0, heads + head, t * BN, bat);
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.v[vs][blk], map, &sm.v_full[vs], blk * HB, heads + head, t * BN, bat);
       }
     }
   } else if (warp == WARP_MMA) {
@@ -304,8 +321,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sm.k[st]);
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk)
-          mma_ss(tmem + COL_S, smem_desc(q_addr + kk * 32, 16, 1024), smem_desc(k_addr + kk * 32, 16, 1024), IDESC_S, kk > 0);
+        for (int blk = 0; blk < NBLK; ++blk)
+#pragma unroll
+          for (int kk = 0; kk < HB / 16; ++kk)
+            mma_ss(tmem + COL_S, smem_desc(q_addr + blk * BLK_BYTES + kk * 32, 16, 1024),
+                   smem_desc(k_addr + blk * BLK_BYTES + kk * 32, 16, 1024), IDESC_S, (blk | kk) > 0);
         tc_commit(&sm.k_empty[st]);
         tc_commit(&sm.s_full);
       };
@@ -323,9 +343,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_fence_after();
         const uint32_t v_addr = smem_u32(sm.v[st]);
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          mma_ts(tmem + COL_O, tmem + COL_P + kk * 8, smem_desc(v_addr + kk * 2048, 16384, 1024), IDESC_PV,
-                 (j > 0 || kk > 0) ? 1u : 0u);
+        for (int blk = 0; blk < NBLK; ++blk)
+#pragma unroll
+          for (int kk = 0; kk < BN / 16; ++kk)
+            mma_ts(tmem + COL_O + blk * HB, tmem + COL_P + kk * 8, smem_desc(v_addr + blk * BLK_BYTES + kk * 2048, 16384, 1024),
+                   IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&sm.v_empty[st]);
         tc_commit(&sm.pv_done);
       }
@@ -403,13 +425,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       if (j > 0) {
         mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
         tc_fence_after();
-        if (__any_sync(0xffffffffu, moved)) {            // this warp owns O columns [32*half, 32*half + 32)
-          uint32_t o[32];
-          tmem_ld32(lane_base + COL_O + half * 32, o);
-          tmem_wait_ld();
+        if (__any_sync(0xffffffffu, moved)) {            // this warp owns O columns [64*blk + 32*half, +32) of every block
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-          tmem_st32(lane_base + COL_O + half * 32, o);
+          for (int blk = 0; blk < NBLK; ++blk) {
+            uint32_t o[32];
+            tmem_ld32(lane_base + COL_O + blk * HB + half * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st32(lane_base + COL_O + blk * HB + half * 32, o);
+          }
         }
       }
       tmem_st32(lane_base + COL_P + half * (HN / 2), pr);
@@ -424,21 +449,25 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float inv_l = 1.f / (sm.red_sum[0][row] + sm.red_sum[1][row]);
     mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
     tc_fence_after();
-    uint32_t o[32];
-    tmem_ld32(lane_base + COL_O + half * 32, o);
-    tmem_wait_ld();
-    if (q0 + row < lq) {
-      __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + half * 32;
-      const int nvec = (d - half * 32) / 8;       // 16-byte vectors of real (un-padded) head columns in this half
 #pragma unroll
-      for (int vq = 0; vq < 4; ++vq) {
-        if (vq < nvec) {
-          int4 w;
-          w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
-          w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
-          w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
-          w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
-          st_v4(dst + vq * 8, w);
+    for (int blk = 0; blk < NBLK; ++blk) {
+      uint32_t o[32];
+      const int col0 = blk * HB + half * 32;        // first head column of this chunk
+      tmem_ld32(lane_base + COL_O + col0, o);
+      tmem_wait_ld();
+      if (q0 + row < lq) {
+        __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
+        const int nvec = (d - col0) / 8;            // 16-byte vectors of real (un-padded) head columns in this chunk
+#pragma unroll
+        for (int vq = 0; vq < 4; ++vq) {
+          if (vq < nvec) {
+            int4 w;
+            w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
+            w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
+            w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
+            w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
+            st_v4(dst + vq * 8, w);
+          }
         }
       }
     }
@@ -473,7 +502,7 @@ int make_map(CUtensorMap* m, const void* base, int d, int nheads, int rows, int 
   DF_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   cuuint64_t dims[4] = {(cuuint64_t)d, (cuuint64_t)nheads, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)d * 2, (cuuint64_t)pitch * 2, (cuuint64_t)rows * pitch * 2};
-  cuuint32_t box[4] = {HD, 1, BN, 1};
+  cuuint32_t box[4] = {HB, 1, BN, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -488,7 +517,7 @@ int make_map(CUtensorMap* m, const void* base, int d, int nheads, int rows, int 
 extern "C" int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t slot_bytes, int b, int lseg, int heads,
                                    int d, void* maps_out, void* stream) {
   static_assert(sizeof(CUtensorMap) == DF_TENSORMAP_BYTES, "tensor map size");
-  DF_REQUIRE(d == 64 || d == 40, "df_attn: head dim %d not supported (40, 64)", d);
+  DF_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "df_attn: head dim %d not supported (multiple of 8, <= 192)", d);
   DF_REQUIRE(slot_bytes >= (uint64_t)b * lseg * 2 * heads * d * 2, "df_attn_make_kvmaps: slot too small");
   CUtensorMap host[DF_NBANKS * DF_MAX_WORLD];
   memset(host, 0, sizeof(host));
@@ -507,7 +536,7 @@ extern "C" int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t
 extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps, int b, int lq,
                            int lseg, int heads, int d, int64_t q_pitch, int64_t kv_pitch, int64_t o_pitch, int nseg,
                            int own_seg, const int32_t* seg_rank_host, int idx, int wait_flags, float scale, void* stream) {
-  DF_REQUIRE(d == 64 || d == 40, "df_attn_fwd: head dim %d not supported (40, 64)", d);
+  DF_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "df_attn_fwd: head dim %d not supported (multiple of 8, <= 192)", d);
   DF_REQUIRE(nseg >= 1 && nseg <= DF_MAX_WORLD && own_seg >= 0 && own_seg < nseg, "df_attn_fwd: bad segment layout");
   DF_REQUIRE(nseg == 1 || kvmaps != nullptr, "df_attn_fwd: peer segments need tensor maps (df_attn_make_kvmaps)");
   DF_REQUIRE(q_pitch % 8 == 0 && kv_pitch % 8 == 0 && o_pitch % 8 == 0 && ((uintptr_t)q % 16) == 0 &&
@@ -519,17 +548,23 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   if (int rc = make_map(&tkv, kv_own, d, 2 * heads, lseg, b, kv_pitch)) return rc;
   SegInfo segs;
   for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
-  static bool attr_set = false;
-  const size_t smem_bytes = sizeof(Smem);
-  if (!attr_set) {
-    DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    attr_set = true;
-  }
   const float sc = (scale > 0.f ? scale : 1.f / sqrtf((float)d)) * 1.4426950408889634f;
   dim3 grid((lq + BM - 1) / BM, heads, b);
-  fmha_fwd_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tq, tkv, (const CUtensorMap*)kvmaps, comm, segs,
-                                                                       (__half*)out, lq, lseg, heads, d, o_pitch, nseg,
-                                                                       own_seg, idx, wait_flags, sc);
+  const int nblk = (d + HB - 1) / HB;
+#define DF_LAUNCH_FMHA(NB)                                                                                                  \
+  {                                                                                                                          \
+    static bool attr_set = false;                                                                                            \
+    const size_t smem_bytes = sizeof(SmemT<NB, Cfg<NB>::KST, Cfg<NB>::VST>);                                                 \
+    if (!attr_set) {                                                                                                         \
+      DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
+      attr_set = true;                                                                                                       \
+    }                                                                                                                        \
+    fmha_fwd_kernel<NB><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(                                               \
+        tq, tkv, (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg, own_seg, idx,      \
+        wait_flags, sc);                                                                                                     \
+  }
+  if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
+#undef DF_LAUNCH_FMHA
   DF_CHECK_LAUNCH();
   return 0;
 }

@@ -117,7 +117,8 @@ int df_halo_assemble(df_comm_t comm, const void* x, void* xp, int b, int h, int 
  *      Segment `own_seg` is read from kv_own (this step's fresh projection, pitch kv_pitch elements); every
  *      other segment s is read from the arena slot(read%NB, idx, src=seg_rank[s]) through the tensor maps
  *      prepared by df_attn_make_kvmaps.  wait_flags != 0 makes the kernel wait for the peers' flags itself.
- *      d in {40, 64}; softmax scale is 1/sqrt(d) unless scale > 0. ------------------------------- */
+ *      d: any multiple of 8 up to 192 (SDXL 64; SD1.x 40 / 80 / 160), zero-padded to 64-column blocks by TMA;
+ *      softmax scale is 1/sqrt(d) unless scale > 0. ------------------------------------------------- */
 int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t slot_bytes, int b, int lseg, int heads,
                         int d, void* maps_out /* device, DF_NBANKS*world*DF_TENSORMAP_BYTES */, void* stream);
 int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps,

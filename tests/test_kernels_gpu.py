@@ -32,6 +32,10 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (2, 300, 1000, 3, 64),         # ragged both ways, > STAGES tiles
     (1, 1024, 4096, 10, 64),       # SDXL level-1 shape at 1024^2, n=4 (lq=L/4)
     (1, 130, 200, 2, 40),          # SD1.x head_dim 40 (zero-filled to 64 by TMA)
+    (2, 300, 520, 2, 80),          # SD1.x head_dim 80  -> two 64-column blocks
+    (1, 256, 256, 8, 160),         # SD1.x head_dim 160 -> three 64-column blocks (level 2/3 shape at 1024^2, n=4)
+    (1, 64, 256, 2, 160),          # SD1.x deepest level: fewer q rows than one tile
+    (1, 200, 77, 2, 80),           # SD1.x cross-attention
 ])
 def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)

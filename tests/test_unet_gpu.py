@@ -46,6 +46,12 @@ def test_unet_multi_rank(name, golden_dir):
     _check(case, run_product_unet(case), golden_dir)
 
 
+def test_unet_sd15_multi_rank(golden_dir):
+    """SD1.x topology (DistriSDPipeline path): head dims 40/80/160/160, 1x1-conv projections, no added embeddings."""
+    case = CASES["sd15_w2_nosplit"]
+    _check(case, run_product_unet(case), golden_dir)
+
+
 def test_unet_multi_rank_cuda_graph(golden_dir):
     case = CASES["sdxl_w2_nosplit"]
     _check(case, run_product_unet(case, use_graph=True), golden_dir)

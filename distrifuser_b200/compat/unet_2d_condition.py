@@ -95,6 +95,12 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, encoder_hidden_states=None):
+        if x.is_cuda and x.dtype == torch.float16:
+            from ..ops import add_layernorm          # residual add + LayerNorm fused (one kernel instead of two)
+            _, h = add_layernorm(x, None, self.norm1)
+            x, h = add_layernorm(x, self.attn1(h, encoder_hidden_states=None), self.norm2)
+            x, h = add_layernorm(x, self.attn2(h, encoder_hidden_states=encoder_hidden_states), self.norm3)
+            return x + self.ff(h)
         x = x + self.attn1(self.norm1(x), encoder_hidden_states=None)
         x = x + self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states)
         return x + self.ff(self.norm3(x))

@@ -43,3 +43,104 @@ extern "C" int df_geglu(const void* in, void* out, int64_t rows, int cols, int64
   DF_CHECK_LAUNCH();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused residual add + LayerNorm for BasicTransformerBlock:  s = x + r (written back, fp16);  y = LN(s) * gamma + beta.
+// One warp per token row, the row lives in registers between the statistics and the normalisation, so the pair
+// `x + attn(...)` / `norm(x)` (two torch kernels, 5 HBM passes) becomes one kernel with 4 passes (2 reads, 2 writes).
+namespace {
+
+template <int MAXV>   // MAXV 16-byte vectors per lane: C <= 32 * 8 * MAXV
+__global__ void __launch_bounds__(256) add_layernorm_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
+                                                            __half* __restrict__ s_out, __half* __restrict__ y,
+                                                            const __half* __restrict__ gamma, const __half* __restrict__ beta,
+                                                            int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 3;
+  const __half* xr = x + row * C;
+  const __half* rr = r ? r + row * C : nullptr;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nvec) {
+      int4 a = ld_nc_v4(xr + q * 8);
+      const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+      if (rr) {
+        int4 b = ld_nc_v4(rr + q * 8);
+        const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+        int4 o;
+        __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          o2[j] = __hadd2(a2[j], b2[j]);                 // same fp16 rounding as the eager `x + r`
+          float2 f = __half22float2(o2[j]);
+          v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
+        }
+        if (s_out) st_v4(s_out + row * C + q * 8, o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __half22float2(a2[j]);
+          v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / (float)C;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + 32 * i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { float d = v[i][j] - mean; var = fmaf(d, d, var); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nvec) {
+      int4 g = ld_v4(gamma + q * 8), bt = ld_v4(beta + q * 8);
+      const __half2* g2 = reinterpret_cast<const __half2*>(&g);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&bt);
+      int4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 gg = __half22float2(g2[j]), bb = __half22float2(b2[j]);
+        o2[j] = __floats2half2_rn((v[i][2 * j] - mean) * rstd * gg.x + bb.x, (v[i][2 * j + 1] - mean) * rstd * gg.y + bb.y);
+      }
+      st_v4(y + row * C + q * 8, o);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int df_add_layernorm(const void* x, const void* r, void* s_out, void* y, const void* gamma, const void* beta,
+                                int64_t rows, int C, float eps, void* stream) {
+  DF_REQUIRE(C % 8 == 0 && C <= 32 * 8 * 8, "df_add_layernorm: C=%d not supported (multiple of 8, <= 2048)", C);
+  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)r % 16) == 0 && ((uintptr_t)s_out % 16) == 0 && ((uintptr_t)y % 16) == 0 &&
+                 ((uintptr_t)gamma % 16) == 0 && ((uintptr_t)beta % 16) == 0, "df_add_layernorm: 16-byte alignment required");
+  if (rows == 0) return 0;
+  const int warps = 8;
+  const unsigned grid = (unsigned)((rows + warps - 1) / warps);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nvec = C / 8;
+#define DF_LN(MV) add_layernorm_kernel<MV><<<grid, warps * 32, 0, st>>>((const __half*)x, (const __half*)r, (__half*)s_out, \
+      (__half*)y, (const __half*)gamma, (const __half*)beta, rows, C, eps)
+  if (nvec <= 32 * 2) DF_LN(2); else if (nvec <= 32 * 3) DF_LN(3); else if (nvec <= 32 * 5) DF_LN(5); else DF_LN(8);
+#undef DF_LN
+  DF_CHECK_LAUNCH();
+  return 0;
+}

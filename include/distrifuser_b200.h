@@ -139,6 +139,11 @@ int df_output_gather(df_comm_t comm, const void* strip, void* out, int B, int C,
  *      path inside DistriUNetPP.forward; in:[rows, 2*cols] fp16 (pitch in_pitch elements), out:[rows, cols]. ---- */
 int df_geglu(const void* in, void* out, int64_t rows, int cols, int64_t in_pitch, int64_t out_pitch, void* stream);
 
+/* ---- fused residual add + LayerNorm of BasicTransformerBlock: s = x + r (fp16, written to s_out when non-null; r may
+ *      be null = plain LayerNorm), y = LayerNorm(s) * gamma + beta.  x, r, s_out, y: [rows, C] contiguous fp16. ---- */
+int df_add_layernorm(const void* x, const void* r, void* s_out, void* y, const void* gamma, const void* beta,
+                     int64_t rows, int C, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

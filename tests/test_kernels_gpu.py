@@ -271,3 +271,20 @@ def test_geglu_fused():
     h, g = y.float().chunk(2, -1)
     ref = h * torch.nn.functional.gelu(g)
     assert ((out.float() - ref).abs() <= 2e-3 + 2e-3 * ref.abs()).all()      # one fp16 rounding of the product
+
+
+@pytest.mark.parametrize("C", [320, 640, 1280, 64, 2048])
+@pytest.mark.parametrize("with_res", [True, False])
+def test_add_layernorm_fused(C, with_res):
+    from distrifuser_b200.ops import add_layernorm
+    torch.manual_seed(8)
+    x = torch.randn(3, 77, C, device="cuda").half()
+    r = torch.randn(3, 77, C, device="cuda").half() if with_res else None
+    ln = torch.nn.LayerNorm(C).cuda().half()
+    with torch.no_grad():
+        ln.weight.copy_(1 + 0.1 * torch.randn(C)); ln.bias.copy_(0.1 * torch.randn(C))
+    s, y = add_layernorm(x, r, ln)
+    s_ref = (x + r) if with_res else x
+    assert torch.equal(s, s_ref)
+    y_ref = torch.nn.functional.layer_norm(s_ref.float(), (C,), ln.weight.float(), ln.bias.float(), ln.eps)
+    assert (y.float() - y_ref).abs().max().item() < 6e-3

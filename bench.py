@@ -245,7 +245,10 @@ def run_ours(a):
         peak = peaks.get("bf16_tflops_sustained", 1590.0 * 1395.4 / 1700.9)
         ach = fl / (t_ms * 1e-3) / 1e12 if t_ms > 0 else 0.0
         roof = {"kernel": "fmha_fwd_kernel (self-attention launches)", "bound": "tensor", "achieved": ach, "peak": peak,
-                "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / peak,
+                # dram__bytes_read+write of ONE level-1 launch (b=2, Lq=Lkv=4096, 10 heads) from the ncu --set full capture in
+                # profiles/r1_fmha_lvl1.txt; its algorithmic bytes are 2*b*(2*Lq*C + 2*Lkv*C) = 41.9 MB (the O write stays in L2)
+                "traffic": 33.8e6 if (a.model == "sdxl" and R == 1024 and world == 1) else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
                 "launches": len(sel), "avg_launch_ms": t_ms / max(len(sel), 1), "share_of_image_ms": t_ms,
                 "groupnorm": {"bound": "hbm", "achieved": gn_b / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0,

@@ -187,18 +187,13 @@ class PatchParallelismCommManager:
     def register_output(self, B: int, Cc: int, H: int, W: int):
         self.output_spec = (B, Cc, H, W)
 
-    # ------------------------------------------------------------------ arena creation (utils.py:151-164)
-    def create_buffer(self):
+    # ------------------------------------------------------------------ arena layout (pure host arithmetic)
+    def _layout(self):
+        """Offsets of the symmetric arena: [group flags u32[nt][n] | world flags u32[world]] then DF_NBANKS banks, each
+        holding n source slots per registered tensor and one output image.  Returns (total_bytes, bank_stride)."""
         cfg = self.distri_config
-        assert cfg.device.type == "cuda", "the communication arena needs a CUDA device"
-        L = _lib.lib()
         n, world = cfg.n_device_per_batch, cfg.world_size
         nt = len(self.slot_bytes)
-        if cfg.rank == 0 and cfg.verbose:
-            print(f"Create buffer with {self.numel / 1e6:.3f}M parameters for {nt} tensors on each device.")
-            for layer_type, numel in self.numel_dict.items():
-                print(f"  {layer_type}: {numel / 1e6:.3f}M parameters")
-        # header: group flags [nt][n] u32, world flags [world] u32
         self._flags_group_off = 0
         self._flags_world_off = _align(4 * max(nt, 1) * n, 256)
         header = _align(self._flags_world_off + 4 * world, 1024)
@@ -212,7 +207,20 @@ class PatchParallelismCommManager:
             B, Cc, H, W = self.output_spec
             off += _align(B * Cc * H * W * 2, 1024)
         bank_stride = _align(off - header, 1024)
-        total = header + NBANKS * bank_stride
+        return header + NBANKS * bank_stride, bank_stride
+
+    # ------------------------------------------------------------------ arena creation (utils.py:151-164)
+    def create_buffer(self):
+        cfg = self.distri_config
+        assert cfg.device.type == "cuda", "the communication arena needs a CUDA device"
+        L = _lib.lib()
+        n, world = cfg.n_device_per_batch, cfg.world_size
+        nt = len(self.slot_bytes)
+        if cfg.rank == 0 and cfg.verbose:
+            print(f"Create buffer with {self.numel / 1e6:.3f}M parameters for {nt} tensors on each device.")
+            for layer_type, numel in self.numel_dict.items():
+                print(f"  {layer_type}: {numel / 1e6:.3f}M parameters")
+        total, bank_stride = self._layout()
         # tensor_off is relative to the arena base; bank k adds k*bank_stride
         ptr = C.c_void_p()
         handle = (C.c_ubyte * _lib.IPC_HANDLE_BYTES)()

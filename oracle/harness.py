@@ -207,3 +207,61 @@ def run_unet(case, impl="oracle"):
         for a, b in zip(per_rank[0], per_rank[r]):
             assert torch.equal(a, b), "final output must be identical on all ranks (distri_sdxl_unet_pp.py:166-168)"
     return per_rank[0]
+
+
+# ---------------------------------------------------------------------------------------------- denoising trajectory
+class _OracleUNetAdapter:
+    """Gives OracleUNetPP the call signature the latent pipeline uses (unet(x, t, encoder_hidden_states=..., ...)[0])."""
+
+    def __init__(self, model, config):
+        self.model, self.config = model, config
+
+    def set_counter(self, c):
+        self.model.set_counter(c)
+
+    def __call__(self, sample, timestep, encoder_hidden_states=None, added_cond_kwargs=None, return_dict=False):
+        t = timestep
+        if torch.is_tensor(t) and t.ndim == 0:
+            t = t.expand(sample.shape[0])
+        return (self.model(sample, t, encoder_hidden_states, added_cond_kwargs=added_cond_kwargs),)
+
+
+def _traj_worker(rank, case, port, outdir, num_steps, guidance):
+    _paths("oracle")
+    from oracle import pp_modules as P
+    from oracle import workloads as W
+    from distrifuser_b200.compat.pipeline import SyntheticLatentPipeline      # the denoising loop itself is shared code:
+    _init(rank, case.world_size, port)                                       # only the UNet path differs between the arms
+    cfg = W.DuckConfig(case.world_size, rank, height=8 * case.latent, width=8 * case.latent,
+                       do_classifier_free_guidance=case.cfg, split_batch=case.split_batch,
+                       warmup_steps=case.warmup_steps, comm_checkpoint=case.comm_checkpoint, mode=case.mode)
+    if case.world_size > 1:
+        _groups(cfg)
+    ucfg = W.unet_config(case.family)
+    unet = W.make_unet(case.family, case.weight_seed)
+    model = P.OracleUNetPP(unet, cfg)
+    model.prepare(W.unet_inputs(case, 0, ucfg))
+    pipe = SyntheticLatentPipeline(_OracleUNetAdapter(model, unet.config), sdxl=ucfg.get("addition_embed_type") == "text_time",
+                                   device="cpu", dtype=torch.float32)
+    model.set_counter(0)
+    g = torch.Generator().manual_seed(case.input_seed)
+    with torch.no_grad():
+        lat = pipe(prompt="a photo", height=8 * case.latent, width=8 * case.latent, num_inference_steps=num_steps,
+                   guidance_scale=guidance, generator=g).images
+    torch.save(lat, os.path.join(outdir, f"rank{rank}.pt"))
+    if case.world_size > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_trajectory(case, num_steps=8, guidance=5.0):
+    """Final latents of a `num_steps` Euler trajectory with the ORACLE UNet path (fp32 CPU) -> [1,4,S,S]."""
+    with tempfile.TemporaryDirectory() as d:
+        if case.world_size == 1:
+            _traj_worker(0, case, 0, d, num_steps, guidance)
+        else:
+            mp.spawn(_traj_worker, args=(case, free_port(), d, num_steps, guidance), nprocs=case.world_size, join=True)
+        outs = [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(case.world_size)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    return outs[0]

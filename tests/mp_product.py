@@ -70,3 +70,44 @@ def run_product_unet(case, use_graph=False):
         else:
             mp.spawn(_worker, args=(case, free_port(), d, use_graph), nprocs=case.world_size, join=True)
         return [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(case.world_size)]
+
+
+def _traj_worker(rank, case, port, outdir, num_steps, guidance, use_graph):
+    from torch import distributed as dist
+    world = case.world_size
+    if world > 1:
+        if torch.cuda.device_count() < world:
+            os.environ["DISTRIFUSER_B200_SHARE_GPU"] = "1"
+        os.environ["LOCAL_RANK"] = str(rank)
+        dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
+    from oracle import workloads as W
+    from distrifuser_b200.compat.unet_2d_condition import UNet2DConditionModel
+    from distrifuser_b200.pipelines import DistriSDPipeline, DistriSDXLPipeline
+    from distrifuser_b200.utils import DistriConfig
+    cfg = DistriConfig(height=8 * case.latent, width=8 * case.latent, do_classifier_free_guidance=case.cfg,
+                       split_batch=case.split_batch, warmup_steps=case.warmup_steps, mode=case.mode, use_cuda_graph=use_graph)
+    ucfg = W.unet_config(case.family)
+    unet = UNet2DConditionModel(**ucfg)
+    unet.load_state_dict(W.make_unet(case.family, case.weight_seed).state_dict(), strict=True)
+    cls = DistriSDXLPipeline if ucfg.get("addition_embed_type") == "text_time" else DistriSDPipeline
+    pipe = cls.from_synthetic(cfg, unet=unet)
+    g = torch.Generator().manual_seed(case.input_seed)
+    lat = pipe(prompt="a photo", num_inference_steps=num_steps, guidance_scale=guidance, generator=g).images     # public API
+    torch.cuda.synchronize()
+    torch.save(lat.float().cpu(), os.path.join(outdir, f"rank{rank}.pt"))
+    if world > 1:
+        dist.barrier()
+        if pipe.comm_manager is not None:
+            pipe.comm_manager.close()
+        dist.destroy_process_group()
+
+
+def run_product_trajectory(case, num_steps=8, guidance=5.0, use_graph=True):
+    from oracle.harness import free_port
+    from torch import multiprocessing as mp
+    with tempfile.TemporaryDirectory() as d:
+        if case.world_size == 1:
+            _traj_worker(0, case, 0, d, num_steps, guidance, use_graph)
+        else:
+            mp.spawn(_traj_worker, args=(case, free_port(), d, num_steps, guidance, use_graph), nprocs=case.world_size, join=True)
+        return [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(case.world_size)]

@@ -97,35 +97,36 @@ __device__ __forceinline__ void signal_when_last(const df_comm_t& c, int idx, ui
   }
 }
 
-__global__ void __launch_bounds__(256) publish_kernel(df_comm_t c, const char* __restrict__ src, uint64_t rows,
-                                                      uint64_t vec_per_row, uint64_t src_pitch, uint64_t tensor_off,
-                                                      uint64_t slot_bytes, int idx, uint32_t peer_mask) {
+// 128 threads x <= 32 registers: a publication CTA fits next to two resident attention CTAs (2 x 320 threads x 96 regs =
+// 61 440 of the 65 536 registers) instead of displacing one of them for the whole transfer.
+__global__ void __launch_bounds__(128, 16) publish_kernel(df_comm_t c, const char* __restrict__ src, uint64_t rows,
+                                                          uint64_t vec_per_row, uint64_t src_pitch, uint64_t tensor_off,
+                                                          uint64_t slot_bytes, int idx, uint32_t peer_mask) {
   const uint32_t epoch = c.clock[0];
-  char* dst[DF_MAX_WORLD];
-  int np = 0;
-  for (int p = 0; p < c.world; ++p)
-    if (peer_mask >> p & 1) dst[np++] = slot_ptr(c, p, epoch, tensor_off, slot_bytes, c.rank);
   const uint64_t total = rows * vec_per_row;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  constexpr int U = 4;
+  const uint64_t bank_off = (uint64_t)(epoch % DF_NBANKS) * c.bank_stride + tensor_off + (uint64_t)c.rank * slot_bytes;
+  constexpr int U = 2;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + (U - 1) * stride < total; i += U * stride) {
     int4 v[U];
-    uint64_t off[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       uint64_t j = i + u * stride, r = j / vec_per_row, q = j - r * vec_per_row;
-      off[u] = j * 16;
       v[u] = ld_nc_v4(src + r * src_pitch + q * 16);
     }
+    for (int p = 0; p < c.world; ++p) {
+      if (!(peer_mask >> p & 1)) continue;
+      char* dst = (char*)c.base[p] + bank_off;
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      for (int p = 0; p < np; ++p) st_v4(dst[p] + off[u], v[u]);
+      for (int u = 0; u < U; ++u) st_v4(dst + (i + u * stride) * 16, v[u]);
+    }
   }
   for (; i < total; i += stride) {
     uint64_t r = i / vec_per_row, q = i - r * vec_per_row;
     int4 v = ld_nc_v4(src + r * src_pitch + q * 16);
-    for (int p = 0; p < np; ++p) st_v4(dst[p] + i * 16, v);
+    for (int p = 0; p < c.world; ++p)
+      if (peer_mask >> p & 1) st_v4((char*)c.base[p] + bank_off + i * 16, v);
   }
   signal_when_last(c, idx, peer_mask, epoch);
 }
@@ -138,10 +139,10 @@ extern "C" int df_slot_publish(df_comm_t comm, const void* src, uint64_t rows, u
   DF_REQUIRE(rows * row_bytes <= slot_bytes, "df_slot_publish: payload larger than the slot");
   if (peer_mask == 0) return 0;
   uint64_t total = rows * (row_bytes / 16);
-  int grid = num_ctas > 0 ? num_ctas : 32;
-  uint64_t need = (total + 255) / 256;
+  int grid = num_ctas > 0 ? num_ctas : 64;
+  uint64_t need = (total + 127) / 128;
   if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-  publish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(comm, (const char*)src, rows, row_bytes / 16, src_pitch,
+  publish_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(comm, (const char*)src, rows, row_bytes / 16, src_pitch,
                                                          tensor_off, slot_bytes, idx, peer_mask);
   DF_CHECK_LAUNCH();
   return 0;

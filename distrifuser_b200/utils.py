@@ -296,12 +296,16 @@ class PatchParallelismCommManager:
     def peers_mask(self) -> int:
         return self.group_mask() & ~(1 << self.distri_config.split_idx())
 
-    def enqueue(self, idx: int, tensor: torch.Tensor, async_stream: bool = True, num_ctas: int = 32):
+    def enqueue(self, idx: int, tensor: torch.Tensor, async_stream: bool = True, num_ctas: int | None = None):
         """Publish `tensor` (this rank's fresh activation of layer idx) into every peer's slot
         (utils.py:181-190: copy into the flat buffer + batched async all_gather)."""
         assert tensor.is_contiguous()
         L = _lib.lib()
         nbytes = tensor.numel() * tensor.element_size()
+        if num_ctas is None:
+            # synchronous steps wait for the data right away: use the whole NVLink; asynchronous publication hides under the
+            # attention that follows and should take few SM slots
+            num_ctas = 64 if async_stream else 296
         main = torch.cuda.current_stream()
         if async_stream:
             self.comm_stream.wait_stream(main)      # fork: publication overlaps the compute that follows

@@ -46,6 +46,13 @@ def test_unet_multi_rank(name, golden_dir):
     _check(case, run_product_unet(case), golden_dir)
 
 
+@pytest.mark.multigpu(8)
+def test_unet_eight_gpus(golden_dir):
+    """cfg2 x patch4 on 8 real GPUs (NVLink peer stores between 8 processes); skipped on smaller boxes."""
+    case = CASES["sdxl_w8_split"]
+    _check(case, run_product_unet(case), golden_dir)
+
+
 def test_unet_sd15_multi_rank(golden_dir):
     """SD1.x topology (DistriSDPipeline path): head dims 40/80/160/160, 1x1-conv projections, no added embeddings."""
     case = CASES["sd15_w2_nosplit"]

@@ -42,7 +42,8 @@ def free_port():
 
 
 def _init(rank, world, port):
-    torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))
+    # tiny parity workloads: more than ~16 OpenMP threads only adds synchronisation overhead (64-thread hosts ran 10x slower)
+    torch.set_num_threads(max(1, min(16, (os.cpu_count() or 8) // world)))
     if world > 1:
         dist.init_process_group("gloo", rank=rank, world_size=world, init_method=f"tcp://127.0.0.1:{port}")
 

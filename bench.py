@@ -29,6 +29,7 @@ for p in (ROOT,):
         sys.path.insert(0, p)
 
 STEPS_PER_IMAGE = 50
+print_json = print
 METRIC = "SDXL 50-step latency (ms/image)"
 
 
@@ -136,7 +137,7 @@ def run_reference(a):
             "cpu_baseline": {"value": ms_image, "unit": "ms/image", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ms_image, "unit": "ms/image", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print_json(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -275,13 +276,27 @@ def run_ours(a):
                 "roofline": roof, "cpu_baseline": cpu, "exposed_comm": exposed,
                 "e2e": {"value": ms_image_e2e, "unit": "ms/image", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_h.numel() * 4},
                 "gpu_launches": launches, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        print_json(json.dumps(line))
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
     a = parse()
+    # exactly ONE line on stdout: libraries (e.g. "NCCL version ..." at communicator creation) write there too, so the real
+    # stdout is parked and fd 1 points at stderr until the JSON line is emitted
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real_stdout, "w")
+
+    def emit(line: str):
+        out.write(line + "\n")
+        out.flush()
+
+    global print_json
+    print_json = emit
     if a.impl == "reference":
         run_reference(a)
     else:

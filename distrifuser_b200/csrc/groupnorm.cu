@@ -63,11 +63,9 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
 __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
                                                        float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
                                                        int ppc, GnExchange ex) {
-  extern __shared__ float acc[];  // [G][2], reused as float2 mine[bG] by the last CTA
+  extern __shared__ float2 ch[];  // [lanes][C] per-channel (sum, sum of squares); reused as float2 mine[bG] by the last CTA
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * G; i += blockDim.x) acc[i] = 0.f;
-  __syncthreads();
   const int v = tid % V, pl = tid / V;
   if (pl < lanes) {
     const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
@@ -95,26 +93,31 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) { float t = f[j] + ad[j]; s[j] += t; ss[j] = fmaf(t, t, ss[j]); }
     }
-    // fold the 8 channels into their groups (runs of equal group id), one shared atomic per run
-    const int cpg = C / G;
-    int g_run = (v * 8) / cpg;
-    float rs = 0.f, rss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      int g = (v * 8 + j) / cpg;
-      if (g != g_run) {
-        atomicAdd(&acc[2 * g_run], rs);
-        atomicAdd(&acc[2 * g_run + 1], rss);
-        g_run = g; rs = 0.f; rss = 0.f;
-      }
-      rs += s[j]; rss += ss[j];
-    }
-    atomicAdd(&acc[2 * g_run], rs);
-    atomicAdd(&acc[2 * g_run + 1], rss);
+    for (int j = 0; j < 8; ++j) ch[(size_t)pl * C + v * 8 + j] = make_float2(s[j], ss[j]);
   }
   __syncthreads();
-  for (int g = tid; g < G; g += blockDim.x)
-    partial[((size_t)b * nchunk + chunk) * G + g] = make_float2(acc[2 * g], acc[2 * g + 1]);
+  // fold channels x pixel-lanes into the G groups in a FIXED order (no atomics: results are bit-reproducible run to run)
+  __shared__ float2 fold[256];
+  const int cpg = C / G;
+  const int parts = min(256 / G, 32);
+  if (tid < parts * G) {
+    const int g = tid % G, part = tid / G;
+    const int per_group = cpg * lanes;
+    float a = 0.f, q = 0.f;
+    for (int e = part; e < per_group; e += parts) {
+      const int pl2 = e / cpg, cc = e - pl2 * cpg;
+      const float2 t = ch[(size_t)pl2 * C + g * cpg + cc];
+      a += t.x; q += t.y;
+    }
+    fold[part * G + g] = make_float2(a, q);
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += blockDim.x) {
+    float a = 0.f, q = 0.f;
+    for (int part = 0; part < parts; ++part) { a += fold[part * G + g].x; q += fold[part * G + g].y; }
+    partial[((size_t)b * nchunk + chunk) * G + g] = make_float2(a, q);
+  }
   // last CTA of the grid finishes the job: reduce the partials, exchange with the patch group, write (mean, rstd)
   __shared__ bool is_last;
   __threadfence();
@@ -127,7 +130,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  gn_exchange(ex, partial, G, nchunk, reinterpret_cast<float2*>(acc));
+  gn_exchange(ex, partial, G, nchunk, ch);
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
@@ -275,7 +278,7 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)addend % 16) == 0,
              "df_groupnorm_fwd: x / y / addend must be 16-byte aligned");
   DF_REQUIRE(mode >= 0 && mode <= 3, "df_groupnorm_fwd: bad mode %d", mode);
-  DF_REQUIRE(b * groups <= 512 && groups <= 256, "df_groupnorm_fwd: b*groups = %d exceeds the exchange buffer", b * groups);
+  DF_REQUIRE(b * groups <= 512 && groups <= 128, "df_groupnorm_fwd: b*groups = %d exceeds the exchange buffer", b * groups);
   DF_REQUIRE(mode == 0 || (slot_bytes >= (uint64_t)b * groups * 8 && (group_mask >> comm.rank & 1)),
              "df_groupnorm_fwd: statistics slot too small or rank outside its own group");
   cudaStream_t st = (cudaStream_t)stream;
@@ -292,7 +295,8 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   ex.bessel = bessel ? (float)((double)ne / (double)(ne - 1)) : 1.f;
   ex.eps = eps; ex.mode = mode; ex.neg_fb = neg_var_fallback; ex.idx = idx;
   ex.tensor_off = tensor_off; ex.slot_bytes = slot_bytes; ex.group_mask = group_mask;
-  size_t smem = (size_t)(2 * groups > 2 * b * groups ? 2 * groups : 2 * b * groups) * sizeof(float);
+  size_t smem = (size_t)p.lanes * C * sizeof(float2);           // <= 32 KiB (lanes * C <= 4096)
+  if (smem < (size_t)b * groups * sizeof(float2)) smem = (size_t)b * groups * sizeof(float2);
   gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, partial, hw, C, groups,
                                                              p.V, p.lanes, p.ppc, ex);
   DF_CHECK_LAUNCH();

@@ -150,6 +150,7 @@ class PatchParallelismCommManager:
         self.handles = None
         # B200 path state
         self.slot_bytes: list[int] = []
+        self.dtypes: list[torch.dtype] = []
         self.tensor_off: list[int] = []
         self.layer_types: list[str] = []
         self.output_spec = None          # (B, C, H, W) of the final epsilon, registered by DistriUNetPP
@@ -181,6 +182,7 @@ class PatchParallelismCommManager:
             self.numel_dict[layer_type] = self.numel_dict.get(layer_type, 0) + numel
         esize = torch.empty((), dtype=torch_dtype).element_size()
         self.slot_bytes.append(_align(slot_bytes if slot_bytes is not None else numel * esize, 256))
+        self.dtypes.append(torch_dtype)
         self.layer_types.append(layer_type or "")
         return len(self.starts) - 1
 
@@ -261,13 +263,10 @@ class PatchParallelismCommManager:
         self.group, self.world, self.bank_stride = g, w, bank_stride
         self.comm_stream = torch.cuda.Stream(device=cfg.device, priority=-1)
         self.handles = [None for _ in range(nt)]
-        self.buffer_list = [self._bank_view(0, r) for r in range(n)]
+        self.buffer_list = [self.arena for _ in range(n)]     # non-None marks "buffers created" (utils.py:160-163); views: get_buffer_list
         if world > 1:
             dist.barrier()          # every arena is mapped everywhere before the first peer store
         torch.cuda.synchronize(cfg.device)
-
-    def _bank_view(self, bank: int, src: int):
-        return self.arena  # flat view; per-tensor views come from get_buffer_list
 
     def get_buffer_list(self, idx: int, bank: int | None = None) -> list[torch.Tensor]:
         """Per-peer views of tensor `idx` (utils.py:166-168).  `bank` defaults to the bank of the last published
@@ -275,12 +274,13 @@ class PatchParallelismCommManager:
         cfg = self.distri_config
         if bank is None:
             bank = int(self.clock[0].item()) % NBANKS
-        esize = torch.empty((), dtype=self.torch_dtype).element_size()
+        dtype = self.dtypes[idx]
+        esize = torch.empty((), dtype=dtype).element_size()
         out = []
         for s in range(cfg.n_device_per_batch):
             o = bank * self.bank_stride + self.tensor_off[idx] + s * self.slot_bytes[idx]
             nb = (self.ends[idx] - self.starts[idx]) * esize
-            out.append(self.arena[o:o + nb].view(self.torch_dtype).view(self.shapes[idx]))
+            out.append(self.arena[o:o + nb].view(dtype).view(self.shapes[idx]))
         return out
 
     # ------------------------------------------------------------------ step protocol

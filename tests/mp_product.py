@@ -93,7 +93,12 @@ def _traj_worker(rank, case, port, outdir, num_steps, guidance, use_graph):
     pipe = cls.from_synthetic(cfg, unet=unet)
     g = torch.Generator().manual_seed(case.input_seed)
     lat = pipe(prompt="a photo", num_inference_steps=num_steps, guidance_scale=guidance, generator=g).images     # public API
+    # a second image with the same seed must reproduce the first bit for bit: nothing (epoch banks, text-KV cache, stale
+    # activations, graph state) may leak from one image into the next (pipelines.py:57 resets the counters)
+    g2 = torch.Generator().manual_seed(case.input_seed)
+    lat2 = pipe(prompt="a photo", num_inference_steps=num_steps, guidance_scale=guidance, generator=g2).images
     torch.cuda.synchronize()
+    assert torch.equal(lat, lat2), "second image with the same seed differs from the first"
     torch.save(lat.float().cpu(), os.path.join(outdir, f"rank{rank}.pt"))
     if world > 1:
         dist.barrier()

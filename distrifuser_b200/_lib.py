@@ -17,7 +17,7 @@ TENSORMAP_BYTES = 128
 EXPORTS = (
     "df_last_error", "df_version", "df_device_sm_count", "df_symm_alloc", "df_symm_open", "df_symm_close",
     "df_symm_free", "df_step_begin", "df_slot_publish", "df_slot_wait", "df_groupnorm_scratch_bytes",
-    "df_groupnorm_fwd", "df_halo_push", "df_halo_assemble", "df_attn_make_kvmaps", "df_attn_fwd",
+    "df_groupnorm_fwd", "df_halo_push", "df_halo_assemble", "df_attn_make_kvmaps", "df_attn_workspace_bytes", "df_attn_fwd",
     "df_output_gather", "df_geglu", "df_add_layernorm",
 )
 
@@ -56,8 +56,10 @@ def lib():
         L.df_halo_push.argtypes = [DfComm, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, vp]
         L.df_halo_assemble.argtypes = [DfComm, vp, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, i32, vp]
         L.df_attn_make_kvmaps.argtypes = [DfComm, u64, u64, i32, i32, i32, i32, vp, vp]
+        L.df_attn_workspace_bytes.argtypes = [i32, i32, i32, i32, i32, i32]
+        L.df_attn_workspace_bytes.restype = C.c_size_t
         L.df_attn_fwd.argtypes = [DfComm, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i64, i64, i32, i32,
-                                  C.POINTER(C.c_int32), i32, i32, f32, vp]
+                                  C.POINTER(C.c_int32), i32, i32, f32, vp, C.c_size_t, vp]
         L.df_geglu.argtypes = [vp, vp, i64, i32, i64, i64, vp]
         L.df_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]
         L.df_output_gather.argtypes = [DfComm, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, u64, vp]

@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<NBLK>::CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
-                float scale_log2) {
+                float scale_log2, int kv_splits, float* __restrict__ part_o, float2* __restrict__ part_ml) {
   constexpr int KSTAGES = Cfg<NBLK>::KST, VSTAGES = Cfg<NBLK>::VST;
   constexpr uint32_t TMEM_COLS = Cfg<NBLK>::TMEM, TILE_BYTES = NBLK * BLK_BYTES;
   using Smem = SmemT<NBLK, KSTAGES, VSTAGES>;
@@ -256,9 +256,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * BM, head = blockIdx.y, bat = blockIdx.z;
+  // split-KV (small grids: the K/V range of one (batch, head, q-tile) is shared by `kv_splits` CTAs, combined afterwards)
+  const int q0 = blockIdx.x * BM, head = blockIdx.y, bat = blockIdx.z / kv_splits, split = blockIdx.z % kv_splits;
   const int tps = (lseg + BN - 1) / BN;  // tiles per segment
-  const int T = nseg * tps;
+  const int T_all = nseg * tps;
+  const int j_begin = (int)((long long)split * T_all / kv_splits);
+  const int T = (int)((long long)(split + 1) * T_all / kv_splits) - j_begin;   // tiles of this CTA (>= 1: kv_splits <= T_all)
 
   if (warp == WARP_MMA && lane == 0) {
     mbar_init(&sm.q_full, 1);
@@ -289,7 +292,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
-      int so = 0, t = 0;                       // segment order index, tile inside the segment (no divisions in the loop)
+      int so = j_begin / tps, t = j_begin - so * tps;   // segment order index, tile inside the segment (one division, outside the loop)
       for (int j = 0; j < T; ++j, ++t) {
         if (t == tps) { t = 0; ++so; }
         int seg = own_seg + so;
@@ -297,7 +300,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const void* map = &tm_kv_own;
         if (seg != own_seg) {
           const int r = segs.rank[seg];
-          if (t == 0 && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
+          if ((t == 0 || j == 0) && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
           map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
         }
         const int ks = j % KSTAGES, vs = j % VSTAGES;
@@ -361,7 +364,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr int HN = BN / 2;                                     // S columns per thread
     float m_ref = -INFINITY;                                       // max used as exponent reference (raw S units)
     float l = 0.f;                                                 // partial row sum over this thread's columns
-    int t = 0;                                                     // tile inside the current segment
+    int t = j_begin % tps;                                         // tile inside the current segment
     for (int j = 0; j < T; ++j, ++t) {
       if (t == tps) t = 0;
       const int valid = min(BN, lseg - t * BN) - half * HN;        // valid columns inside this thread's half
@@ -446,9 +449,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // ---- epilogue: O / l -> fp16 -> HBM (each half-row warp writes its 32 columns)
     sm.red_sum[half][row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-    const float inv_l = 1.f / (sm.red_sum[0][row] + sm.red_sum[1][row]);
+    const float l_row = sm.red_sum[0][row] + sm.red_sum[1][row];
+    const float inv_l = 1.f / l_row;
     mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
     tc_fence_after();
+    const int64_t prow = (((int64_t)split * gridDim.z / kv_splits + bat) * heads + head) * lq + q0 + row;   // partial-result row
+    if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
       uint32_t o[32];
@@ -456,17 +462,24 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tmem_ld32(lane_base + COL_O + col0, o);
       tmem_wait_ld();
       if (q0 + row < lq) {
-        __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
-        const int nvec = (d - col0) / 8;            // 16-byte vectors of real (un-padded) head columns in this chunk
+        if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
+          float* dst = part_o + prow * (NBLK * HB) + col0;
 #pragma unroll
-        for (int vq = 0; vq < 4; ++vq) {
-          if (vq < nvec) {
-            int4 w;
-            w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
-            w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
-            w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
-            w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
-            st_v4(dst + vq * 8, w);
+          for (int vq = 0; vq < 8; ++vq)
+            st_v4(dst + vq * 4, make_int4((int)o[vq * 4], (int)o[vq * 4 + 1], (int)o[vq * 4 + 2], (int)o[vq * 4 + 3]));
+        } else {
+          __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
+          const int nvec = (d - col0) / 8;          // 16-byte vectors of real (un-padded) head columns in this chunk
+#pragma unroll
+          for (int vq = 0; vq < 4; ++vq) {
+            if (vq < nvec) {
+              int4 w;
+              w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
+              w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
+              w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
+              w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
+              st_v4(dst + vq * 8, w);
+            }
           }
         }
       }
@@ -476,6 +489,33 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   if (warp == WARP_TMA) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// Combine the split-KV partials: out = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max_s m_s) * scale_log2).
+// One warp per (batch, head, q-row); lanes stride over the head columns.
+__global__ void __launch_bounds__(256) fmha_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
+                                                           __half* __restrict__ out, int64_t rows_per_split, int lq, int heads,
+                                                           int d, int hd_pad, int64_t o_pitch, int kv_splits, float scale_log2) {
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (bat * heads + head) * lq + q
+  if (r >= rows_per_split) return;
+  const int lane = threadIdx.x & 31;
+  float m = -INFINITY;
+  for (int s = 0; s < kv_splits; ++s) m = fmaxf(m, part_ml[s * rows_per_split + r].x);
+  float w[8], denom = 0.f;
+  for (int s = 0; s < kv_splits; ++s) {
+    const float2 ml = part_ml[s * rows_per_split + r];
+    w[s] = ex2((ml.x - m) * scale_log2);
+    denom = fmaf(w[s], ml.y, denom);
+  }
+  const float inv = 1.f / denom;
+  const int64_t bh = r / lq, q = r - bh * lq;
+  const int64_t bat = bh / heads, head = bh - bat * heads;
+  __half* dst = out + (bat * lq + q) * o_pitch + head * d;
+  for (int c = lane; c < d; c += 32) {
+    float acc = 0.f;
+    for (int s = 0; s < kv_splits; ++s) acc = fmaf(w[s], part_o[(s * rows_per_split + r) * hd_pad + c], acc);
+    dst[c] = __float2half_rn(acc * inv);
   }
 }
 
@@ -533,9 +573,42 @@ extern "C" int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t
   return 0;
 }
 
+namespace {
+// How many CTAs share the K/V range of one (batch, head, q-tile).  Measured (tools/bench_attn.py --no-split): for the short
+// K/V ranges of SDXL at 1024^2 (8-32 tiles) the extra combine launch costs more than the split saves (23.6 vs 18.4 us at
+// b=1, Lq=256, Lkv=1024), so the split is reserved for grids that fill < 1/4 of the resident CTA slots AND keep >= 8 tiles
+// per CTA (long K/V, very short Q).
+int plan_kv_splits(int b, int lq, int lseg, int nseg, int heads, int d) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  const int nblk = (d + HB - 1) / HB;
+  const long long slots = (long long)sms * (nblk == 1 ? 2 : 1);
+  const long long ctas = (long long)((lq + BM - 1) / BM) * heads * b;
+  const int t_all = nseg * ((lseg + BN - 1) / BN);
+  if (ctas * 4 > slots || t_all < 16) return 1;
+  long long s = slots / ctas;
+  if (s > 8) s = 8;
+  if (s > t_all / 8) s = t_all / 8;
+  return s < 2 ? 1 : (int)s;
+}
+}  // namespace
+
+extern "C" size_t df_attn_workspace_bytes(int b, int lq, int lseg, int nseg, int heads, int d) {
+  const int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
+  if (splits == 1) return 0;
+  const int hd_pad = ((d + HB - 1) / HB) * HB;
+  return (size_t)splits * b * heads * lq * ((size_t)hd_pad * sizeof(float) + sizeof(float2)) + 256;
+}
+
 extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps, int b, int lq,
                            int lseg, int heads, int d, int64_t q_pitch, int64_t kv_pitch, int64_t o_pitch, int nseg,
-                           int own_seg, const int32_t* seg_rank_host, int idx, int wait_flags, float scale, void* stream) {
+                           int own_seg, const int32_t* seg_rank_host, int idx, int wait_flags, float scale, void* workspace,
+                           size_t workspace_bytes, void* stream) {
   DF_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "df_attn_fwd: head dim %d not supported (multiple of 8, <= 192)", d);
   DF_REQUIRE(nseg >= 1 && nseg <= DF_MAX_WORLD && own_seg >= 0 && own_seg < nseg, "df_attn_fwd: bad segment layout");
   DF_REQUIRE(nseg == 1 || kvmaps != nullptr, "df_attn_fwd: peer segments need tensor maps (df_attn_make_kvmaps)");
@@ -549,8 +622,14 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   SegInfo segs;
   for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
   const float sc = (scale > 0.f ? scale : 1.f / sqrtf((float)d)) * 1.4426950408889634f;
-  dim3 grid((lq + BM - 1) / BM, heads, b);
   const int nblk = (d + HB - 1) / HB;
+  int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < df_attn_workspace_bytes(b, lq, lseg, nseg, heads, d))) splits = 1;
+  DF_REQUIRE((long long)b * splits <= 65535, "df_attn_fwd: grid too large");
+  const int64_t rows = (int64_t)b * heads * lq;
+  float2* part_ml = (float2*)workspace;                                   // [splits][rows]
+  float* part_o = splits > 1 ? (float*)((char*)workspace + (((size_t)splits * rows * sizeof(float2) + 255) / 256) * 256) : nullptr;
+  dim3 grid((lq + BM - 1) / BM, heads, b * splits);
 #define DF_LAUNCH_FMHA(NB)                                                                                                  \
   {                                                                                                                          \
     static bool attr_set = false;                                                                                            \
@@ -561,10 +640,16 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
     }                                                                                                                        \
     fmha_fwd_kernel<NB><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(                                               \
         tq, tkv, (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg, own_seg, idx,      \
-        wait_flags, sc);                                                                                                     \
+        wait_flags, sc, splits, part_o, part_ml);                                                                            \
   }
   if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA
+  DF_CHECK_LAUNCH();
+  if (splits > 1) {
+    const unsigned cg = (unsigned)((rows + 7) / 8);
+    fmha_combine_kernel<<<cg, 256, 0, (cudaStream_t)stream>>>(part_o, part_ml, (__half*)out, rows, lq, heads, d, nblk * HB, o_pitch,
+                                                              splits, sc);
+  }
   DF_CHECK_LAUNCH();
   return 0;
 }

@@ -33,6 +33,7 @@ class DistriAttentionPP(BaseModule):
                 to_kv.bias[out_size:].copy_(to_v.bias)
         self.to_kv = to_kv
         self._kvmaps = None
+        self._workspace = None           # split-KV scratch for small per-rank grids (df_attn_workspace_bytes)
 
     def _attend(self, q, kv_own, lseg, nseg, own_seg, wait_flags, kind="self"):
         """softmax(q k^T / sqrt(d)) v over `nseg` K/V segments of `lseg` rows each; q:[b,lq,C], kv_own:[b,lseg,2C]."""
@@ -47,14 +48,19 @@ class DistriAttentionPP(BaseModule):
         else:
             comm, maps = _lib.null_comm(), None
         seg_rank = (C.c_int32 * _lib.MAX_WORLD)(*range(_lib.MAX_WORLD))
+        L = _lib.lib()
+        ws_bytes = L.df_attn_workspace_bytes(b, lq, lseg, nseg, heads, d)
+        if ws_bytes and (self._workspace is None or self._workspace.numel() < ws_bytes):
+            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
+        ws = self._workspace.data_ptr() if ws_bytes else None
         prof = _lib.PROFILE
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        _lib.check(_lib.lib().df_attn_fwd(comm, q.data_ptr(), kv_own.data_ptr(), out.data_ptr(), maps, b, lq, lseg,
-                                          heads, d, q.stride(1), kv_own.stride(1), out.stride(1), nseg, own_seg,
-                                          seg_rank, self.idx or 0, int(wait_flags), 0.0,
-                                          torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+        _lib.check(L.df_attn_fwd(comm, q.data_ptr(), kv_own.data_ptr(), out.data_ptr(), maps, b, lq, lseg,
+                                 heads, d, q.stride(1), kv_own.stride(1), out.stride(1), nseg, own_seg,
+                                 seg_rank, self.idx or 0, int(wait_flags), 0.0, ws, ws_bytes,
+                                 torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
         if prof is not None:
             e1.record()
             prof.append(dict(kernel="fmha_fwd_kernel", kind=kind,

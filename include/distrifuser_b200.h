@@ -121,10 +121,14 @@ int df_halo_assemble(df_comm_t comm, const void* x, void* xp, int b, int h, int 
  *      softmax scale is 1/sqrt(d) unless scale > 0. ------------------------------------------------- */
 int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t slot_bytes, int b, int lseg, int heads,
                         int d, void* maps_out /* device, DF_NBANKS*world*DF_TENSORMAP_BYTES */, void* stream);
+/* Small grids (short per-rank Q at n >= 2) split the K/V range of a q-tile over several CTAs and combine the partial
+ * (O, max, sum) triples in a second kernel; that needs df_attn_workspace_bytes() of scratch (0 = single pass).  Passing a
+ * null / too small workspace simply disables the split. */
+size_t df_attn_workspace_bytes(int b, int lq, int lseg, int nseg, int heads, int d);
 int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps,
                 int b, int lq, int lseg, int heads, int d, int64_t q_pitch, int64_t kv_pitch, int64_t o_pitch,
                 int nseg, int own_seg, const int32_t* seg_rank_host, int idx, int wait_flags, float scale,
-                void* stream);
+                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- final epsilon gather: replaces the blocking world all_gather + cat(dim=2) at the end of
  *      DistriUNetPP.forward (distrifuser/models/distri_sdxl_unet_pp.py:162-169,186-193).

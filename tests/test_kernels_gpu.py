@@ -18,9 +18,13 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     d = Cq // heads
     out = torch.empty_like(q)
     seg_rank = (C.c_int32 * 8)(*range(8))
-    _lib.check(_lib.lib().df_attn_fwd(comm or _lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), maps, b, lq,
-                                      lseg or kv.shape[1], heads, d, q.stride(1), kv.stride(1), out.stride(1), nseg, own,
-                                      seg_rank, idx, wait, 0.0, torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+    L = _lib.lib()
+    ws_bytes = L.df_attn_workspace_bytes(b, lq, lseg or kv.shape[1], nseg, heads, d)      # > 0: the split-KV path is taken
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    _lib.check(L.df_attn_fwd(comm or _lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), maps, b, lq,
+                             lseg or kv.shape[1], heads, d, q.stride(1), kv.stride(1), out.stride(1), nseg, own,
+                             seg_rank, idx, wait, 0.0, ws.data_ptr() if ws_bytes else None, ws_bytes,
+                             torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
     torch.cuda.synchronize()
     return out
 
@@ -36,6 +40,9 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (1, 256, 256, 8, 160),         # SD1.x head_dim 160 -> three 64-column blocks (level 2/3 shape at 1024^2, n=4)
     (1, 64, 256, 2, 160),          # SD1.x deepest level: fewer q rows than one tile
     (1, 200, 77, 2, 80),           # SD1.x cross-attention
+    (1, 256, 8192, 4, 64),         # tiny grid, long K/V: split-KV (8 CTAs per q-tile) + combine kernel
+    (1, 130, 4100, 3, 64),         # split-KV with ragged q and k/v tiles
+    (1, 100, 3000, 2, 40),         # split-KV, zero-padded head dim
 ])
 def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)
@@ -46,6 +53,15 @@ def test_attention_single_segment(b, lq, lk, heads, d):
     ref = sdpa_ref(q, kv[..., :Cq], kv[..., Cq:], heads)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-3, f"max abs err {err}"
+
+
+def test_attention_split_kv_is_planned_for_small_grids():
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > 0         # 8 CTAs on 296 slots, 64 K/V tiles
+    assert L.df_attn_workspace_bytes(1, 256, 1024, 1, 20, 64) == 0       # short K/V: the combine launch would cost more
+    assert L.df_attn_workspace_bytes(2, 4096, 4096, 1, 10, 64) == 0      # 640 CTAs: single pass
+    assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile
 
 
 def test_attention_large_logits_rescale():

@@ -14,6 +14,7 @@ SHAPES = {  # name: (b, lq, lkv, heads, d)
     "1024_l1": (2, 4096, 4096, 10, 64), "1024_l2": (2, 1024, 1024, 20, 64),
     "3840n4_l2": (1, 3600, 14400, 20, 64), "3840n4_l1": (1, 14400, 57600, 10, 64),
     "2048n2_l1": (1, 8192, 16384, 10, 64), "cross_l2": (2, 1024, 77, 20, 64),
+    "1024n4_l2": (1, 256, 1024, 20, 64), "1024n4_l1": (1, 1024, 4096, 10, 64), "1024n2_l2": (1, 512, 1024, 20, 64),
 }
 
 
@@ -22,6 +23,7 @@ def main():
     ap.add_argument("--shapes", default="1024_l1,1024_l2,3840n4_l2,2048n2_l1")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--profile", action="store_true")
+    ap.add_argument("--no-split", action="store_true", help="disable split-KV (A/B)")
     a = ap.parse_args()
     from distrifuser_b200 import _lib
     L = _lib.lib()
@@ -33,11 +35,14 @@ def main():
         kv = torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16)
         out = torch.empty_like(q)
         seg = (C.c_int32 * 8)(*range(8))
+        ws_bytes = 0 if a.no_split else L.df_attn_workspace_bytes(b, lq, lk, 1, h, d)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
         st = torch.cuda.current_stream().cuda_stream
 
         def run():
             _lib.check(L.df_attn_fwd(_lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), None, b, lq, lk, h, d,
-                                     q.stride(1), kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0, st), "df_attn_fwd")
+                                     q.stride(1), kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0,
+                                     ws.data_ptr() if ws_bytes else None, ws_bytes, st), "df_attn_fwd")
         for _ in range(3):
             run()
         torch.cuda.synchronize()

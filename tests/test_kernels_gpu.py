@@ -44,7 +44,12 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (1, 130, 4100, 3, 64),         # split-KV with ragged q and k/v tiles
     (1, 100, 3000, 2, 40),         # split-KV, zero-padded head dim
 ])
-def test_attention_single_segment(b, lq, lk, heads, d):
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_attention_single_segment(b, lq, lk, heads, d, kernel, monkeypatch):
+    """kernel 1 = fmha_fwd_kernel (one Q tile per CTA, two CTAs per SM); 2 = fmha2_fwd_kernel (two Q tiles per CTA)."""
+    if kernel == 2 and d > 64:
+        pytest.skip("fmha2 covers d <= 64")
+    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
     torch.manual_seed(0)
     Cq = heads * d
     q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16)
@@ -64,8 +69,10 @@ def test_attention_split_kv_is_planned_for_small_grids():
     assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile
 
 
-def test_attention_large_logits_rescale():
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_attention_large_logits_rescale(kernel, monkeypatch):
     """Rows whose running max jumps by > 2^8 between tiles exercise the O-correction path."""
+    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
     torch.manual_seed(1)
     b, lq, lk, heads, d = 1, 128, 512, 1, 64
     q = torch.randn(b, lq, d, device="cuda", dtype=torch.float16) * 4
@@ -77,10 +84,12 @@ def test_attention_large_logits_rescale():
     assert err < 4e-3, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("n,own", [(2, 0), (2, 1), (4, 2)])
-def test_attention_multi_segment_stale_slots(n, own):
+def test_attention_multi_segment_stale_slots(n, own, kernel, monkeypatch):
     """K/V of the peers is read in place from the arena slots of the READ epoch (attn.py:136-138 without the cat)."""
     from distrifuser_b200 import _lib
+    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
     torch.manual_seed(2)
     b, lseg, heads, d = 2, 200, 2, 64
     Cq = heads * d

@@ -60,6 +60,14 @@ struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
 };
 
+#ifdef DF_TRACE
+// cycle-level event trace of CTA (0,0,0) for kernel tuning (tools/trace_attn.py); compiled out by default
+__device__ long long df_trace_buf[64 * 16];
+#define DF_TR(slot, tile) do { if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 64) df_trace_buf[(tile) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DF_TR(slot, tile) do {} while (0)
+#endif
+
 // instruction descriptors (kind::f16, fp16 inputs, fp32 accumulate, M = 128)
 constexpr uint32_t IDESC_S = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);               // K-major A, K-major B
 constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 16) | ((uint32_t)(HB >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);  // B (=V) MN-major, N = 64
@@ -161,12 +169,15 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (j + 1 < T) {
           mbar_wait(&sm.s_free, (uint32_t)j & 1u);   // S_j is in the softmax warps' registers
           tc_fence_after();
+          DF_TR(8, j);
           issue_qk(j + 1);
+          DF_TR(9, j);
         }
         const int st = j % VSTAGES;
         mbar_wait(&sm.p_full, (uint32_t)j & 1u);
         mbar_wait(&sm.v_full[st], (uint32_t)(j / VSTAGES) & 1u);
         tc_fence_after();
+        DF_TR(10, j);
         const uint32_t v_addr = smem_u32(sm.v[st]);
 #pragma unroll
         for (int blk = 0; blk < NBLK; ++blk)
@@ -176,6 +187,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                    IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
         tc_commit(&sm.v_empty[st]);
         tc_commit(&sm.pv_done);
+        DF_TR(11, j);
       }
     }
   } else {
@@ -193,6 +205,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int valid = min(BN, lseg - t * BN) - half * HN;        // valid columns inside this thread's half
       mbar_wait(&sm.s_full, (uint32_t)j & 1u);
       tc_fence_after();
+      if (threadIdx.x == 0) DF_TR(0, j);
       uint32_t sr[HN];
       const uint32_t s_addr = lane_base + COL_S + half * HN;
       tmem_ld32(s_addr + 0, sr + 0);
@@ -201,6 +214,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
+      if (threadIdx.x == 0) DF_TR(1, j);
       if (valid < HN) {                          // ragged last tile of a segment only
         asm volatile("" ::: "memory");            // keep this a real (warp-uniform) branch: if-converted it costs 2 instr / element on every tile
 #pragma unroll
@@ -220,6 +234,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       sm.red_max[j & 1][half][row] = pm;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       const float m_new = max3(pm, sm.red_max[j & 1][half ^ 1][row], m_ref);
+      if (threadIdx.x == 0) DF_TR(2, j);
       // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
       float alpha = 1.f;
       bool moved = false;
@@ -252,9 +267,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float sum0, sum1;
       unpack2(add2(sum2, sum2b), sum0, sum1);
       l += sum0 + sum1;
+      if (threadIdx.x == 0) DF_TR(3, j);
       if (j > 0) {
         mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
         tc_fence_after();
+        if (threadIdx.x == 0) DF_TR(4, j);
         if (__any_sync(0xffffffffu, moved)) {            // this warp owns O columns [64*blk + 32*half, +32) of every block
 #pragma unroll
           for (int blk = 0; blk < NBLK; ++blk) {
@@ -272,6 +289,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full);
+      if (threadIdx.x == 0) DF_TR(5, j);
     }
     // ---- epilogue: O / l -> fp16 -> HBM (each half-row warp writes its 32 columns)
     sm.red_sum[half][row] = l;
@@ -705,6 +723,14 @@ int plan_kv_splits(int b, int lq, int lseg, int nseg, int heads, int d) {
   return s < 2 ? 1 : (int)s;
 }
 }  // namespace
+
+#ifdef DF_TRACE
+extern "C" int df_debug_read_trace(long long* out_host /* 64*16 */) {
+  DF_CHECK_CUDA(cudaDeviceSynchronize());
+  DF_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, df_trace_buf, sizeof(long long) * 64 * 16));
+  return 0;
+}
+#endif
 
 extern "C" int df_debug_fmha2_attrs(int* out /* 6 ints */) {
   cudaFuncAttributes a;

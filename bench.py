@@ -313,7 +313,7 @@ def run_ours(a):
         _lib.PROFILE = None
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:        # reported at N=1 only (rank 0's host cores)
         v, threads, sample, _ = cpu_reference_sample(a.model, R, 1, 1)
         cpu = {"value": v, "unit": "ms/image", "cores": threads, "kind": "port", "sample": sample}
 

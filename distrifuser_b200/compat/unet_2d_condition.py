@@ -94,13 +94,20 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim)
         self.ff = FeedForward(dim)
 
+    def forward_chained(self, x, pending, encoder_hidden_states=None):
+        """Fused path: the block input is `x + pending` (pending = the previous block's feed-forward output, or None); returns
+        (x', pending') with the true output x' + pending', so that the trailing residual add is fused into the next block's
+        first add+LayerNorm kernel."""
+        from ..ops import add_layernorm              # residual add + LayerNorm in one kernel
+        x, h = add_layernorm(x, pending, self.norm1)
+        x, h = add_layernorm(x, self.attn1(h, encoder_hidden_states=None), self.norm2)
+        x, h = add_layernorm(x, self.attn2(h, encoder_hidden_states=encoder_hidden_states), self.norm3)
+        return x, self.ff(h)
+
     def forward(self, x, encoder_hidden_states=None):
         if x.is_cuda and x.dtype == torch.float16:
-            from ..ops import add_layernorm          # residual add + LayerNorm fused (one kernel instead of two)
-            _, h = add_layernorm(x, None, self.norm1)
-            x, h = add_layernorm(x, self.attn1(h, encoder_hidden_states=None), self.norm2)
-            x, h = add_layernorm(x, self.attn2(h, encoder_hidden_states=encoder_hidden_states), self.norm3)
-            return x + self.ff(h)
+            x, pending = self.forward_chained(x, None, encoder_hidden_states)
+            return x + pending
         x = x + self.attn1(self.norm1(x), encoder_hidden_states=None)
         x = x + self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states)
         return x + self.ff(self.norm3(x))
@@ -134,8 +141,14 @@ class Transformer2DModel(nn.Module):
             t = self.proj_in(self._tokens(x))
         else:
             t = self._tokens(self.proj_in(x))
-        for blk in self.transformer_blocks:
-            t = blk(t, encoder_hidden_states=encoder_hidden_states)
+        if t.is_cuda and t.dtype == torch.float16:
+            pending = None
+            for blk in self.transformer_blocks:
+                t, pending = blk.forward_chained(t, pending, encoder_hidden_states)
+            t = t + pending
+        else:
+            for blk in self.transformer_blocks:
+                t = blk(t, encoder_hidden_states=encoder_hidden_states)
         if self.use_linear_projection:
             x = self._image(self.proj_out(t), h, w)
         else:

@@ -732,14 +732,6 @@ extern "C" int df_debug_read_trace(long long* out_host /* 64*16 */) {
 }
 #endif
 
-extern "C" int df_debug_fmha2_attrs(int* out /* 6 ints */) {
-  cudaFuncAttributes a;
-  DF_CHECK_CUDA(cudaFuncGetAttributes(&a, fmha2_fwd_kernel));
-  out[0] = a.numRegs; out[1] = a.maxThreadsPerBlock; out[2] = (int)a.sharedSizeBytes; out[3] = a.maxDynamicSharedSizeBytes;
-  out[4] = (int)a.localSizeBytes; out[5] = (int)sizeof(Smem2);
-  return 0;
-}
-
 extern "C" size_t df_attn_workspace_bytes(int b, int lq, int lseg, int nseg, int heads, int d) {
   const int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
   if (splits == 1) return 0;

@@ -112,8 +112,10 @@ __global__ void __launch_bounds__(128, 16) publish_kernel(df_comm_t c, const cha
     int4 v[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      uint64_t j = i + u * stride, r = j / vec_per_row, q = j - r * vec_per_row;
-      v[u] = ld_nc_v4(src + r * src_pitch + q * 16);
+      const uint64_t j = i + u * stride;
+      uint64_t soff = j * 16;                                      // contiguous source (rows == 1)
+      if (rows > 1) { const uint32_t r = (uint32_t)j / (uint32_t)vec_per_row; soff = (uint64_t)r * src_pitch + (uint64_t)((uint32_t)j - r * (uint32_t)vec_per_row) * 16; }
+      v[u] = ld_nc_v4(src + soff);
     }
     for (int p = 0; p < c.world; ++p) {
       if (!(peer_mask >> p & 1)) continue;
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(128, 16) publish_kernel(df_comm_t c, const cha
     }
   }
   for (; i < total; i += stride) {
-    uint64_t r = i / vec_per_row, q = i - r * vec_per_row;
-    int4 v = ld_nc_v4(src + r * src_pitch + q * 16);
+    uint64_t soff = i * 16;
+    if (rows > 1) { const uint32_t r = (uint32_t)i / (uint32_t)vec_per_row; soff = (uint64_t)r * src_pitch + (uint64_t)((uint32_t)i - r * (uint32_t)vec_per_row) * 16; }
+    int4 v = ld_nc_v4(src + soff);
     for (int p = 0; p < c.world; ++p)
       if (peer_mask >> p & 1) st_v4((char*)c.base[p] + bank_off + i * 16, v);
   }
@@ -137,6 +140,7 @@ extern "C" int df_slot_publish(df_comm_t comm, const void* src, uint64_t rows, u
   DF_REQUIRE(row_bytes % 16 == 0 && ((uintptr_t)src % 16) == 0 && src_pitch % 16 == 0,
              "df_slot_publish: rows must be 16-byte aligned (row_bytes=%llu)", (unsigned long long)row_bytes);
   DF_REQUIRE(rows * row_bytes <= slot_bytes, "df_slot_publish: payload larger than the slot");
+  DF_REQUIRE(rows * (row_bytes / 16) < (1ull << 31), "df_slot_publish: payload too large for 32-bit row arithmetic");
   if (peer_mask == 0) return 0;
   uint64_t total = rows * (row_bytes / 16);
   int grid = num_ctas > 0 ? num_ctas : 64;

@@ -41,7 +41,7 @@ class DistriAttentionPP(BaseModule):
         b, lq, Cq = q.shape
         heads = attn.heads
         d = Cq // heads
-        out = torch.empty_like(q)
+        out = torch.empty((b, lq, Cq), dtype=q.dtype, device=q.device)
         cm = self.comm_manager
         if nseg > 1:
             comm, maps = cm.group, self._kvmaps.data_ptr()
@@ -103,6 +103,22 @@ class DistriCrossAttentionPP(DistriAttentionPP):
 
 
 class DistriSelfAttentionPP(DistriAttentionPP):
+    def __init__(self, module: nn.Module, distri_config: DistriConfig):
+        super().__init__(module, distri_config)
+        # q and k|v read the same activations: one [C -> 3C] GEMM instead of two launches (to_kv is kept: it is the reference's
+        # attribute, attn.py:39, and sizes the registered slot)
+        to_q = module.to_q
+        self._w_qkv = None
+        if isinstance(to_q, nn.Linear) and to_q.bias is None and self.to_kv.bias is None and \
+                to_q.in_features == self.to_kv.in_features and to_q.out_features * 2 == self.to_kv.out_features:
+            self._w_qkv = torch.cat([to_q.weight.data, self.to_kv.weight.data], 0).contiguous()
+
+    def _apply(self, fn, recurse=True):
+        super()._apply(fn, recurse)
+        if self._w_qkv is not None:
+            self._w_qkv = fn(self._w_qkv)          # plain tensor: follows .to() / .half() of the module
+        return self
+
     def forward(self, hidden_states, encoder_hidden_states=None, scale: float = 1.0, *args, **kwargs):
         cfg = self.distri_config
         self._require_cuda_half(hidden_states, "DistriSelfAttentionPP")
@@ -112,8 +128,12 @@ class DistriSelfAttentionPP(DistriAttentionPP):
         cm = self.comm_manager
         if n > 1 and self._recording() and self.idx is None:
             self.idx = cm.register_tensor((b, l, self.to_kv.out_features), hidden_states.dtype, layer_type="attn")  # :185-190
-        q = attn.to_q(hidden_states)                                     # attn.py:121
-        kv = self.to_kv(hidden_states)                                   # attn.py:125
+        if self._w_qkv is not None and self._w_qkv.dtype == hidden_states.dtype:
+            qkv = F.linear(hidden_states, self._w_qkv)                   # attn.py:121,125 in one GEMM
+            q, kv = qkv[..., :c], qkv[..., c:]                           # views: row pitch 3C, no copies
+        else:
+            q = attn.to_q(hidden_states)                                 # attn.py:121
+            kv = self.to_kv(hidden_states)                               # attn.py:125
         if n == 1 or not self._bound():
             # attn.py:127-131: one rank, or buffers not created yet (n identical copies of kv give the same softmax)
             out = self._attend(q, kv, l, 1, 0, False)

@@ -299,9 +299,18 @@ class PatchParallelismCommManager:
     def enqueue(self, idx: int, tensor: torch.Tensor, async_stream: bool = True, num_ctas: int | None = None):
         """Publish `tensor` (this rank's fresh activation of layer idx) into every peer's slot
         (utils.py:181-190: copy into the flat buffer + batched async all_gather)."""
-        assert tensor.is_contiguous()
         L = _lib.lib()
-        nbytes = tensor.numel() * tensor.element_size()
+        esz = tensor.element_size()
+        if tensor.is_contiguous():
+            rows, row_bytes, pitch = 1, tensor.numel() * esz, tensor.numel() * esz
+        else:
+            # a [.., rows, cols] view with a uniform row pitch (e.g. the k|v columns of a fused q|k|v projection)
+            assert tensor.stride(-1) == 1 and tensor.ndim >= 2
+            cols, pitch_el = tensor.shape[-1], tensor.stride(-2)
+            for dim in range(tensor.ndim - 2):
+                assert tensor.stride(dim) == tensor.stride(dim + 1) * tensor.shape[dim + 1], "rows must have one pitch"
+            rows, row_bytes, pitch = tensor.numel() // cols, cols * esz, pitch_el * esz
+        nbytes = rows * row_bytes
         if num_ctas is None:
             # synchronous steps wait for the data right away: use the whole NVLink; asynchronous publication hides under the
             # attention that follows and should take few SM slots
@@ -314,7 +323,7 @@ class PatchParallelismCommManager:
             self._keepalive.append(tensor)
         else:
             stream = main
-        _lib.check(L.df_slot_publish(self.group, tensor.data_ptr(), 1, nbytes, nbytes, self.tensor_off[idx],
+        _lib.check(L.df_slot_publish(self.group, tensor.data_ptr(), rows, row_bytes, pitch, self.tensor_off[idx],
                                      self.slot_bytes[idx], idx, self.peers_mask(), num_ctas, stream.cuda_stream),
                    "df_slot_publish")
 

@@ -313,3 +313,23 @@ def test_add_layernorm_fused(C, with_res):
     assert torch.equal(s, s_ref)
     y_ref = torch.nn.functional.layer_norm(s_ref.float(), (C,), ln.weight.float(), ln.bias.float(), ln.eps)
     assert (y.float() - y_ref).abs().max().item() < 6e-3
+
+
+def test_publish_strided_rows():
+    """k|v columns of a fused q|k|v projection: rows with a pitch larger than the row (df_slot_publish rows > 1)."""
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    n, rows, C3 = 2, 3 * 700, 3 * 256
+    qkv = torch.randn(rows, C3, device="cuda").half()
+    kv = qkv[:, C3 // 3:]
+    nbytes = rows * kv.shape[1] * 2
+    arena = LoopbackArena(n, [nbytes], rank=0)
+    arena.set_clock(pub=2, rd=2)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.df_slot_publish(arena.comm, kv.data_ptr(), rows, kv.shape[1] * 2, C3 * 2, arena.tensor_off[0], arena.slot_bytes[0], 0,
+                                 0b10, 16, st), "publish")
+    torch.cuda.synchronize()
+    got = arena.slot(2, 0, 0, nbytes).view(rows, kv.shape[1])
+    ok = torch.equal(got, kv)
+    arena.close()
+    assert ok

@@ -17,7 +17,7 @@
  *
  * Symmetric arena layout (one per rank, mapped into every peer with CUDA IPC):
  *   bank k in [0, DF_NBANKS): byte offset k * bank_stride; inside a bank every registered tensor has
- *   `world` source slots: slot(k, idx, src) = base + k*bank_stride + tensor_off[idx] + src*slot_bytes[idx].
+ *   one source slot per patch-group member: slot(k, idx, src) = base + k*bank_stride + tensor_off[idx] + src*slot_bytes[idx].
  *   Epoch e (one per UNet call) publishes into bank e % DF_NBANKS and stamps flags[idx*world + src] = e
  *   on the destination rank.  The epoch clock lives in device memory so captured CUDA graphs replay.
  */
@@ -48,15 +48,18 @@ int df_symm_open(const void* ipc_handle_host, void** peer_dptr);
 int df_symm_close(void* peer_dptr);
 int df_symm_free(void* dptr);
 
-/* Communicator descriptor, filled by the host shim and passed BY VALUE to the kernels. */
+/* Communicator descriptor, filled by the host shim and passed BY VALUE to the kernels.  A communicator describes
+ * one GROUP of ranks and indexes its members 0..world-1: the host builds one for the patch group (the ranks that share a
+ * CFG branch: K/V, halo and GroupNorm traffic) and one for the whole world (final epsilon gather); both point into the
+ * same arenas but use separate flag regions.  Every "rank" / mask bit below is an index inside the communicator. */
 typedef struct {
-  void* base[DF_MAX_WORLD];        /* arena base of every world rank, as mapped in THIS process       */
-  uint32_t* flags[DF_MAX_WORLD];   /* flag array of every world rank (inside its arena)               */
-  uint32_t* clock;                 /* this rank's epoch clock: [0]=pub epoch, [1]=read epoch          */
-  uint32_t* tickets;               /* this rank's per-tensor CTA ticket counters (local scratch)      */
-  uint64_t bank_stride;            /* bytes between banks                                              */
-  int32_t world;                   /* world size                                                       */
-  int32_t rank;                    /* this rank (world index)                                          */
+  void* base[DF_MAX_WORLD];        /* arena base of every member, as mapped in THIS process (own = local)  */
+  uint32_t* flags[DF_MAX_WORLD];   /* flag array of every member (inside its arena): flags[idx*world+src]  */
+  uint32_t* clock;                 /* this rank's epoch clock: [0]=publish, [1]=read, [2]=output epoch     */
+  uint32_t* tickets;               /* this rank's per-tensor CTA ticket counters (local scratch, zeroed)   */
+  uint64_t bank_stride;            /* bytes between banks                                                   */
+  int32_t world;                   /* members in this communicator                                          */
+  int32_t rank;                    /* this rank's index in the communicator                                 */
 } df_comm_t;
 
 /* ---- epoch clock: replaces the host-side counter / handle bookkeeping of the comm manager
@@ -68,8 +71,8 @@ int df_step_begin(uint32_t* clock, int kind, void* stream);
 /* ---- activation publication: replaces enqueue()+batched async all_gather (utils.py:170-190) and the
  *      blocking all_gather of synchronous steps (attn.py:133).  Copies `rows` rows of `row_bytes` bytes
  *      (source pitch `src_pitch`) into slot(pub%NB, idx, src=comm.rank) of every rank in `peer_mask`
- *      (bit i = world rank i; may include comm.rank itself) and then stamps their flags with the pub
- *      epoch (release, system scope). ------------------------------------------------------------- */
+ *      (bit i = member i of the communicator; may include comm.rank itself) and then stamps their flags with
+ *      the pub epoch (release, system scope).  rows > 1 publishes a strided [rows, row_bytes] view. ------- */
 int df_slot_publish(df_comm_t comm, const void* src, uint64_t rows, uint64_t row_bytes, uint64_t src_pitch,
                     uint64_t tensor_off, uint64_t slot_bytes, int idx, uint32_t peer_mask, int num_ctas,
                     void* stream);

@@ -7,7 +7,20 @@ using namespace df;
 
 namespace {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+// gelu_erf(x) = x * Phi(x).  erf through Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7: far below the fp16 rounding of the
+// result): 5 FMAs + one MUFU.RCP + one MUFU.EX2 instead of libdevice erff's two-branch polynomial -- the kernel was
+// ALU-bound at 3.1 TB/s with erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float e = p * t * __expf(-z * z);            // 1 - erf(|x|/sqrt2)
+  const float phi = x >= 0.f ? 1.f - 0.5f * e : 0.5f * e;
+  return x * phi;
+}
 
 __global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ in, __half* __restrict__ out, int64_t rows,
                                                     int vec_per_row, int64_t in_pitch, int64_t out_pitch, int cols) {

@@ -1,0 +1,84 @@
+"""CPU checks of the diffusers stand-ins used when `diffusers` is absent (distrifuser_b200/compat): scheduler constants of
+the SD/SDXL configuration and the denoising-loop plumbing of the latent pipeline (CFG duplication, guidance combine)."""
+import math
+
+import torch
+
+from distrifuser_b200.compat.pipeline import SyntheticLatentPipeline
+from distrifuser_b200.compat.schedulers import DDIMScheduler, EulerDiscreteScheduler
+
+
+def test_euler_schedule_constants():
+    s = EulerDiscreteScheduler()
+    s.set_timesteps(50)
+    assert s.timesteps.tolist()[0] == 981 and s.timesteps.tolist()[-1] == 1            # "leading" spacing, steps_offset 1
+    sig = s.sigmas
+    assert len(sig) == 51 and sig[-1] == 0 and all(sig[i] > sig[i + 1] for i in range(50))
+    # sqrt(sigma_max^2 + 1) over the SELECTED timesteps (t=981 -> 13.16; 14.6 is the value before set_timesteps, t=999)
+    assert abs(s.init_noise_sigma - math.sqrt(float(sig[0]) ** 2 + 1)) < 1e-5 and 13.0 < s.init_noise_sigma < 13.4
+    x = torch.randn(1, 4, 8, 8)
+    assert torch.allclose(s.scale_model_input(x), x / math.sqrt(float(sig[0]) ** 2 + 1))
+    prev = s.step(torch.ones_like(x), s.timesteps[0], x)[0]
+    assert torch.allclose(prev, x + (float(sig[1]) - float(sig[0])))
+
+
+def test_ddim_step_is_identity_for_consistent_eps():
+    s = DDIMScheduler()
+    s.set_timesteps(50)
+    x0 = torch.randn(1, 4, 8, 8)
+    eps = torch.randn(1, 4, 8, 8)
+    t = int(s._ts_host[0])
+    a = float(s.alphas_cumprod[t])
+    xt = a ** 0.5 * x0 + (1 - a) ** 0.5 * eps
+    prev = s.step(eps, s.timesteps[0], xt)[0]
+    a_prev = float(s.alphas_cumprod[t - s._ratio])
+    assert torch.allclose(prev, a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * eps, atol=1e-5)
+
+
+class _FakeUNet:
+    """Returns eps = cond-dependent constant so the CFG combine is observable; records the calls it receives."""
+
+    def __init__(self):
+        from types import SimpleNamespace
+        self.config = SimpleNamespace(in_channels=4, cross_attention_dim=16, projection_class_embeddings_input_dim=6 * 8 + 12,
+                                      addition_time_embed_dim=8)
+        self.calls = []
+
+    def __call__(self, x, t, encoder_hidden_states=None, added_cond_kwargs=None, return_dict=False):
+        self.calls.append((tuple(x.shape), float(t), tuple(encoder_hidden_states.shape),
+                           None if added_cond_kwargs is None else tuple(added_cond_kwargs["time_ids"].shape)))
+        eps = torch.zeros_like(x)
+        if x.shape[0] == 2:
+            eps[1] = 1.0                      # cond branch predicts 1, uncond 0 -> combined = guidance_scale
+        return (eps,)
+
+
+def test_latent_pipeline_loop_and_cfg():
+    unet = _FakeUNet()
+    pipe = SyntheticLatentPipeline(unet, sdxl=True, device="cpu", dtype=torch.float32)
+    g = torch.Generator().manual_seed(0)
+    out = pipe(prompt="x", height=64, width=64, num_inference_steps=5, guidance_scale=5.0, generator=g).images
+    assert out.shape == (1, 4, 8, 8) and len(unet.calls) == 5
+    shp, t0, ehs, ids = unet.calls[0]
+    assert shp == (2, 4, 8, 8) and ehs == (2, 77, 16) and ids == (2, 6)                 # CFG batch duplication, SDXL time ids
+    assert [c[1] for c in unet.calls] == sorted([c[1] for c in unet.calls], reverse=True)
+    # with eps == guidance_scale everywhere, Euler gives x_T + 5 * (0 - sigma_0)
+    s = EulerDiscreteScheduler(); s.set_timesteps(5)
+    g2 = torch.Generator().manual_seed(0)
+    x_T = torch.randn((1, 4, 8, 8), generator=g2) * s.init_noise_sigma
+    assert torch.allclose(out, x_T - 5.0 * float(s.sigmas[0]), atol=1e-4)
+    # guidance off: single batch, no duplication
+    unet.calls.clear()
+    pipe(prompt="x", height=64, width=64, num_inference_steps=2, guidance_scale=1.0, generator=g)
+    assert unet.calls[0][0] == (1, 4, 8, 8)
+
+
+def test_launch_summarizer_families(tmp_path):
+    import importlib.util, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("summ", os.path.join(root, "tools", "summarize_launches.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    assert m.family("void <unnamed>::fmha_fwd_kernel<1>(CUtensorMap_st ...)").startswith("OURS fmha")
+    assert m.family("<unnamed>::add_layernorm_kernel<5>(...)").startswith("OURS add_layernorm")
+    assert m.family("nvjet_hsh_192x256_64x5_2x1_2cta_v_bz_bias_TNT") == "library GEMM (cuBLAS)"
+    assert "elementwise" in m.family("void at::vectorized_elementwise_kernel<8, at::CUDAFunctor_add<c10::Half>>")

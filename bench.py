@@ -3,13 +3,16 @@
 
     python bench.py --gpus 1 --steps 5 --warmup 3                       # ours, one GPU
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...                                # the reference's CPU path (oracle port)
+    python bench.py --impl reference ...                                # the reference's CPU path (oracle port), host cores
+    python bench.py --impl reference-gpu ...                            # extra: the UNMODIFIED reference on the same GPUs
 
-A "step" is one full image: 50 denoising steps (CFG pair per step) of the SDXL UNet at --resolution (default
-1024x1024 = BASELINE.json configs[1]'s workload; strong scaling: the same image at every N), Euler scheduler,
-4 warm-up synchronous steps (DistriConfig defaults), synthetic inputs, random-init weights (no network for
-checkpoints).  `value` times the loop with inputs resident in HBM; `e2e` times DistriSDXLPipeline.__call__ with
-pinned-host prompt embeddings / latents copied in and the final latents copied out inside the timed region.
+A "step" of our arm is one full image: 50 denoising steps (CFG pair per step) of the SDXL UNet at --resolution (default
+1024x1024 = BASELINE.json configs[1]'s workload; strong scaling: the same image at every N), Euler scheduler, 4 warm-up
+synchronous steps (DistriConfig defaults), synthetic inputs, random-init weights (no network for checkpoints).
+`value` times the loop with inputs resident in HBM; `e2e` times DistriSDXLPipeline.__call__ with pinned-host prompt
+embeddings / latents copied in and the final latents copied out inside the timed region.  Extra blocks of the same JSON
+line: `roofline` (tcgen05 attention kernel at the step's shapes), `exposed_comm` (synchronous / asynchronous step split),
+`hires` (the north-star 3840x3840 image at the same N), `cpu_baseline` (N=1).
 """
 from __future__ import annotations
 
@@ -20,7 +23,6 @@ import statistics
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -38,7 +40,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--resolution", type=int, default=1024)
     ap.add_argument("--model", default="sdxl", choices=["sdxl", "sd15"])
     ap.add_argument("--mode", default="corrected_async_gn")
@@ -46,6 +48,10 @@ def parse():
     ap.add_argument("--no-cuda-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exposed-comm", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-hires", action="store_true", help="skip the 3840x3840 block")
+    ap.add_argument("--hires-resolution", type=int, default=3840)
+    ap.add_argument("--cpu-budget-s", type=float, default=200.0, help="wall budget of the CPU reference arm")
     return ap.parse_args()
 
 
@@ -90,106 +96,361 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def load_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-FLOPS_STEP = {"sdxl": {512: 3.18e12, 1024: 13.52e12, 2048: 35.91e12 * 2, 3840: 232.46e12 * 2}}   # per CFG pair
-
-
-def cpu_reference_sample(model: str, resolution: int, reps: int, warm: int):
-    """Times the oracle port of the reference's CPU path (fp32, world_size 1: stock UNet forward exactly as
-    DistriUNetPP.forward runs it, distri_sdxl_unet_pp.py:118-133) on the host cores: one denoise step (CFG pair) of
-    the full-size UNet at 512x512 -- BASELINE.json configs[0], the reference's own CPU-runnable case -- and scales it
-    to ms/image of the requested resolution by the per-step FLOP ratio x 50 steps."""
+def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_warm: int, budget_s: float):
+    """Times the oracle port of the reference's CPU path (fp32, world_size 1: the stock UNet forward exactly as
+    DistriUNetPP.forward runs it when nothing is wrapped, distri_sdxl_unet_pp.py:118-133) on ALL host cores, at the benched
+    resolution.  One SAMPLE = one denoise step of ONE classifier-free-guidance branch (batch 1) of the full-size UNet; the
+    reference's single-device step runs the two branches as one batch-2 forward (twice the work on a CPU), so
+    ms/image = sample x 2 branches x 50 steps.  Samples are REAL forwards at the benched size (no FLOP-ratio scaling);
+    as many of the requested warm-up / timed samples as fit the wall budget are run, and the count that ran is reported."""
     sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_stub"))
     import torch
     from oracle import pp_modules, workloads
-    threads = torch.get_num_threads()
+    t_begin = time.perf_counter()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)                      # torchrun exports OMP_NUM_THREADS=1: do not inherit it silently
     family = "sdxl" if model == "sdxl" else "sd15"
+    latent = resolution // 8
     unet = workloads.make_unet(family, 0)
-    cfg = workloads.DuckConfig(1, 0, height=512, width=512)
+    cfg = workloads.DuckConfig(1, 0, height=resolution, width=resolution, do_classifier_free_guidance=False)
     wrapped = pp_modules.OracleUNetPP(unet, cfg)
-    case = workloads.UNetCase("cpu", family=family, world_size=1, latent=64)
+    case = workloads.UNetCase("cpu", family=family, world_size=1, latent=latent, cfg=False)
     inp = workloads.unet_inputs(case, 0, workloads.unet_config(family))
-    times = []
-    for i in range(warm + reps):
+    build_s = time.perf_counter() - t_begin
+    times, warm_done, warm_t = [], 0, 0.0
+
+    def one():
         t0 = time.perf_counter()
         wrapped(**inp)
-        dt = time.perf_counter() - t0
-        if i >= warm:
-            times.append(dt)
-    step_s = sum(times) / len(times)
-    ratio = FLOPS_STEP["sdxl"].get(resolution, 13.52e12 * (resolution / 1024) ** 2) / FLOPS_STEP["sdxl"][512] if model == "sdxl" else (resolution / 512) ** 2
-    ms_image = step_s * ratio * STEPS_PER_IMAGE * 1e3
-    sample = (f"{len(times)} timed + {warm} warm-up single denoise steps (CFG pair, fp32) of the full {family} UNet at 512x512 "
-              f"on {threads} host threads: {step_s:.2f} s/step; scaled x{ratio:.2f} (FLOP ratio to {resolution}^2) x50 steps")
-    return ms_image, threads, sample, step_s
+        return time.perf_counter() - t0
+
+    with torch.no_grad():
+        for i in range(max(1, want_warm)):          # at least one warm-up sample; more only while they fit 40 % of the budget
+            if i > 0 and (time.perf_counter() - t_begin) + warm_t > 0.4 * budget_s:
+                break
+            warm_t = one()
+            warm_done += 1
+        while len(times) < max(1, want_timed):      # at least one timed sample; more only while the next one fits the budget
+            if times and (time.perf_counter() - t_begin) + times[-1] > budget_s:
+                break
+            times.append(one())
+    sample_s = sum(times) / len(times)
+    ms_image = sample_s * 2 * STEPS_PER_IMAGE * 1e3
+    sample = (f"{len(times)} timed + {warm_done} warm-up samples; one sample = one denoise step of one CFG branch (batch 1, fp32) of "
+              f"the full {family} UNet at {resolution}x{resolution} on {threads} host threads: {sample_s:.2f} s/sample "
+              f"(min {min(times):.2f}, max {max(times):.2f}); ms/image = sample x 2 branches x {STEPS_PER_IMAGE} steps; "
+              f"model build {build_s:.0f} s outside the timed region")
+    return dict(ms_image=ms_image, threads=threads, sample=sample, sample_s=sample_s, timed=len(times), warm=warm_done)
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ms_image, threads, sample, step_s = cpu_reference_sample(a.model, a.resolution, max(1, a.steps), min(a.warmup, 1))
-    line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_image, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+    r = cpu_reference_samples(a.model, a.resolution, max(1, a.steps), max(1, a.warmup), a.cpu_budget_s)
+    ms_image = r["ms_image"]
+    line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": a.gpus, "steps": r["timed"], "warmup": r["warm"],
+            "steps_requested": a.steps, "warmup_requested": a.warmup,
+            "ms_per_step": r["sample_s"] * 1e3, "ms_per_step_is": "one bounded sample (see cpu_baseline.sample), not one image",
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"SDXL UNet {a.resolution}x{a.resolution}, 50-step Euler, CFG batch 2, reference CPU path (oracle port, world_size 1)",
+            "config": {"workload": f"{a.model.upper()} UNet {a.resolution}x{a.resolution}, 50-step Euler, CFG batch 2, reference CPU path "
+                                   f"(oracle port, world_size 1), bounded sample of the same workload",
                        "inputs_larger_than_l2": True},
-            "cpu_baseline": {"value": ms_image, "unit": "ms/image", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": ms_image, "unit": "ms/image", "cores": r["threads"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": ms_image, "unit": "ms/image", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print_json(json.dumps(line))
 
 
-# ------------------------------------------------------------------------------------------------ ours
-def run_ours(a):
+# ------------------------------------------------------------------------------------------------ the unmodified reference on the GPU(s)
+def run_reference_gpu(a):
+    """SURVEY 8(d)(ii) "same-box GPU baseline": the UNMODIFIED reference package (baseline/_ref, installed with
+    `pip install --no-deps --target`) -- its DistriConfig, PatchParallelismCommManager (NCCL all_gather), pp modules,
+    DistriUNetPP and DistriSDXLPipeline.prepare()/CUDA graphs -- on the same synthetic fp16 workload.  diffusers is absent, so
+    the UNet it wraps is the diffusers-0.24 restatement of oracle/diffusers_stub (torch SDPA / cuDNN / eager GroupNorm) and
+    the denoising loop is the same latent-space stand-in our arm uses.  Reported as an extra arm; never the `reference` slot."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "distrifuser")):
+        print_json(json.dumps({"impl": "reference-gpu", "unavailable": "baseline/_ref/distrifuser is not installed"}))
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "diffusers_stub"))
+    sys.path.insert(0, ref_dir)
     import torch
     from torch import distributed as dist
-    from distrifuser_b200 import _lib
-    from distrifuser_b200.compat.schedulers import DDIMScheduler, EulerDiscreteScheduler
-    from distrifuser_b200.pipelines import DistriSDPipeline, DistriSDXLPipeline
-    from distrifuser_b200.utils import DistriConfig
-    _lib.lib()
-    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU"
+    from distrifuser.pipelines import DistriSDXLPipeline as RefPipeline          # the reference, unmodified
+    from distrifuser.utils import DistriConfig as RefConfig
+    from oracle import workloads
+    from distrifuser_b200.compat.pipeline import SyntheticLatentPipeline        # diffusers' loop stand-in (shared by both arms)
     R = a.resolution
-    cfg = DistriConfig(height=R, width=R, mode=a.mode, split_batch=not a.no_split_batch, use_cuda_graph=not a.no_cuda_graph)
-    rank, world = cfg.rank, cfg.world_size
-    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE is {world} (launch with torch.distributed.run)"
+    if "RANK" in os.environ:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    cfg = RefConfig(height=R, width=R, mode=a.mode, split_batch=not a.no_split_batch, use_cuda_graph=not a.no_cuda_graph)
     dev = cfg.device
-    cls = DistriSDXLPipeline if a.model == "sdxl" else DistriSDPipeline
-    pipe = cls.from_synthetic(cfg, seed=0)
+    unet = workloads.make_unet("sdxl", 0, dtype=torch.float16).to(dev)
+    from distrifuser.models.distri_sdxl_unet_pp import DistriUNetPP as RefUNetPP
+    unet = RefUNetPP(unet, cfg)
+    pipe = RefPipeline(SyntheticLatentPipeline(unet, None, sdxl=True, device=dev, dtype=torch.float16), cfg)
     pipe.set_progress_bar_config(disable=True)
-    ucfg = pipe.pipeline.unet.config
-    B = 2
-    g = torch.Generator().manual_seed(1234)                                   # scripts/run_sdxl.py:32
-    embeds_h = torch.randn(B, 77, ucfg.cross_attention_dim, generator=g).half().pin_memory()
-    pooled_h = None
-    if a.model == "sdxl":
-        pooled_h = torch.randn(B, ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim, generator=g).half().pin_memory()
-    lat_h = torch.randn(1, 4, R // 8, R // 8, generator=g).pin_memory()
-    out_h = torch.empty(1, 4, R // 8, R // 8).pin_memory()
-    embeds_d, lat_d = embeds_h.to(dev), lat_h.to(dev)
-    pooled_d = pooled_h.to(dev) if pooled_h is not None else None
+    g = torch.Generator().manual_seed(1234)
+    ucfg = workloads.unet_config("sdxl")
+    embeds = torch.randn(2, 77, ucfg["cross_attention_dim"], generator=g).half().to(dev)
+    pooled = torch.randn(2, ucfg["projection_class_embeddings_input_dim"] - 6 * ucfg["addition_time_embed_dim"], generator=g).half().to(dev)
+    lat = torch.randn(1, 4, R // 8, R // 8, generator=g).to(dev)
+    world = cfg.world_size
 
-    def image(host: bool):
-        kw = dict(num_inference_steps=STEPS_PER_IMAGE, guidance_scale=5.0, output_type="latent")
-        if host:
-            r = pipe(prompt_embeds=embeds_h, pooled_prompt_embeds=pooled_h, latents=lat_h, **kw)
-            out_h.copy_(r.images, non_blocking=True)
-        else:
-            r = pipe(prompt_embeds=embeds_d, pooled_prompt_embeds=pooled_d, latents=lat_d, **kw)
-        return r
+    def image():
+        return pipe(prompt_embeds=embeds, pooled_prompt_embeds=pooled, latents=lat, num_inference_steps=STEPS_PER_IMAGE,
+                    guidance_scale=5.0, output_type="latent")
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(host: bool, k: int):
+    for _ in range(max(1, a.warmup)):
+        image()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        image()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_image = ms.item() / a.steps
+    if cfg.rank == 0:
+        line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": max(1, a.warmup),
+                "ms_per_step": ms_image, "ms_per_denoise_step": ms_image / STEPS_PER_IMAGE, "higher_is_better": False,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference-gpu",
+                "config": {"workload": f"SDXL UNet {R}x{R}, 50-step Euler, CFG batch 2, random-init weights; UNMODIFIED reference "
+                                       f"(baseline/_ref) over the diffusers-0.24 stub UNet, NCCL, torch SDPA / cuDNN",
+                           "mode": cfg.mode, "cuda_graph": cfg.use_cuda_graph, "n_device_per_batch": cfg.n_device_per_batch}}
+        print_json(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def build_pipe(a, resolution):
+    import torch
+    from distrifuser_b200.pipelines import DistriSDPipeline, DistriSDXLPipeline
+    from distrifuser_b200.utils import DistriConfig
+    cfg = DistriConfig(height=resolution, width=resolution, mode=a.mode, split_batch=not a.no_split_batch,
+                       use_cuda_graph=not a.no_cuda_graph)
+    cls = DistriSDXLPipeline if a.model == "sdxl" else DistriSDPipeline
+    pipe = cls.from_synthetic(cfg, seed=0)
+    pipe.set_progress_bar_config(disable=True)
+    return cfg, pipe
+
+
+def make_inputs(a, pipe, dev, R):
+    import torch
+    ucfg = pipe.pipeline.unet.config
+    g = torch.Generator().manual_seed(1234)                                   # scripts/run_sdxl.py:32
+    embeds_h = torch.randn(2, 77, ucfg.cross_attention_dim, generator=g).half().pin_memory()
+    pooled_h = None
+    if a.model == "sdxl":
+        pooled_h = torch.randn(2, ucfg.projection_class_embeddings_input_dim - 6 * ucfg.addition_time_embed_dim, generator=g).half().pin_memory()
+    lat_h = torch.randn(1, 4, R // 8, R // 8, generator=g).pin_memory()
+    out_h = torch.empty(1, 4, R // 8, R // 8).pin_memory()
+    return dict(embeds_h=embeds_h, pooled_h=pooled_h, lat_h=lat_h, out_h=out_h, embeds_d=embeds_h.to(dev), lat_d=lat_h.to(dev),
+                pooled_d=pooled_h.to(dev) if pooled_h is not None else None)
+
+
+def attention_roofline(a, pipe, cfg, image, ms_image, dev, world, R):
+    """Dominant-kernel roofline (fmha_fwd_kernel, self-attention launches).
+      (1) one instrumented eager image records the shape of every attention / GroupNorm launch of the model;
+      (2) every distinct self-attention shape is then timed with CUDA events as a CUDA graph of `count` back-to-back launches
+          on ROTATING buffers (total footprint > L2), i.e. the kernel's average launch duration at exactly the step's shapes
+          without the host-launch gaps that eager in-model events pick up for 30-us kernels.
+    The kernel is timed ALONE (a graph of attention launches only), so the BURST tensor peak of MEASURED_PEAKS.json is the
+    denominator; the fraction of the sustained figure is printed beside it."""
+    import ctypes as C
+    import torch
+    from distrifuser_b200 import _lib
+    saved = cfg.use_cuda_graph
+    try:
+        cfg.use_cuda_graph = False
+        _lib.PROFILE = []
+        image(False)
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+    finally:
+        cfg.use_cuda_graph = saved
+        _lib.PROFILE = None
+    gn = [p for p in prof if p["kind"] == "gn"]
+    gn_ms = sum(p["start"].elapsed_time(p["end"]) for p in gn)
+    gn_b = sum(p["bytes"] for p in gn)
+    per_step = {}
+    for p in prof:
+        if p["kind"] == "self":
+            per_step[p["shape"]] = per_step.get(p["shape"], 0) + 1
+    per_step = {k: v // STEPS_PER_IMAGE for k, v in per_step.items()}          # launches of that shape per denoise step
+    L = _lib.lib()
+    seg = (C.c_int32 * 8)(*range(8))
+    total_ms_step, total_fl_step, detail = 0.0, 0.0, []
+    traffic_db = {}
+    try:
+        traffic_db = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
+    traffic_sum, traffic_n = 0.0, 0
+    for (bb, lq_, lkv_, heads_, d_), count in per_step.items():
+        Cq = heads_ * d_
+        nbuf = count
+        while nbuf > 4 and nbuf * (2 * bb * lq_ * Cq + bb * lkv_ * 2 * Cq) * 2 > 8e9:    # 3840^2 shapes: bound the footprint
+            nbuf //= 2
+        qs = [torch.randn(bb, lq_, Cq, device=dev, dtype=torch.float16) for _ in range(nbuf)]
+        kvs = [torch.randn(bb, lkv_, 2 * Cq, device=dev, dtype=torch.float16) for _ in range(nbuf)]
+        outs = [torch.empty_like(q_) for q_ in qs]
+        side = torch.cuda.Stream(device=dev)
+
+        def launch_all():
+            st = torch.cuda.current_stream().cuda_stream
+            for i in range(count):
+                q_, kv_, o_ = qs[i % nbuf], kvs[i % nbuf], outs[i % nbuf]
+                _lib.check(L.df_attn_fwd(_lib.null_comm(), q_.data_ptr(), kv_.data_ptr(), o_.data_ptr(), None, bb, lq_, lkv_,
+                                         heads_, d_, q_.stride(1), kv_.stride(1), o_.stride(1), 1, 0, seg, 0, 0, 0.0, None, 0,
+                                         st), "df_attn_fwd")
+        with torch.cuda.stream(side):
+            launch_all()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            launch_all()
+        for _ in range(2):
+            g.replay()
+        reps = 5 if lq_ * lkv_ < 1e8 else 2
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_launch = e0.elapsed_time(e1) / reps / count
+        fl = 4.0 * bb * lq_ * lkv_ * Cq
+        total_ms_step += ms_launch * count
+        total_fl_step += fl * count
+        key = f"fmha_fwd_kernel b{bb} lq{lq_} lkv{lkv_} h{heads_} d{d_}"
+        tr = traffic_db.get(key, {}).get("dram_bytes")
+        if tr is not None:
+            traffic_sum += tr * count
+            traffic_n += count
+        detail.append({"shape": {"b": bb, "lq": lq_, "lkv": lkv_, "heads": heads_, "d": d_}, "launches_per_step": count,
+                       "avg_launch_ms": ms_launch, "tflops": fl / ms_launch / 1e9,
+                       "algorithmic_bytes": 2.0 * (2 * bb * lq_ * Cq + bb * lkv_ * 2 * Cq), "ncu_dram_bytes": tr,
+                       "footprint_mb": nbuf * (2 * bb * lq_ * Cq + bb * lkv_ * 2 * Cq) * 2 / 1e6})
+        del qs, kvs, outs, g
+    peaks = load_peaks()
+    burst = peaks.get("bf16_tflops", 1590.0)
+    sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+    ach = total_fl_step / (total_ms_step * 1e-3) / 1e12 if total_ms_step > 0 else 0.0
+    n_launch = sum(per_step.values())
+    roof = {"kernel": "fmha_fwd_kernel (self-attention launches of one denoise step)", "bound": "tensor", "achieved": ach,
+            "peak": burst, "unit": "TFLOP/s", "frac": ach / burst,
+            "frac_of_sustained": ach / sustained, "peak_sustained": sustained,
+            # average per launch over the step's launches, from the ncu --set full captures summarised in profiles/ncu_traffic.json
+            # (dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each shape); null when a shape has no capture
+            "traffic": (traffic_sum / traffic_n) if traffic_n == n_launch and n_launch else None,
+            "traffic_source": "profiles/ncu_traffic.json" if traffic_n == n_launch and n_launch else None,
+            "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst: the kernel is timed alone), of measured" if peaks
+                            else "fallback 1.59 PFLOP/s burst (B200_PROFILING.md), of fallback"),
+            "launches_per_step": n_launch, "avg_launch_ms": total_ms_step / max(n_launch, 1),
+            "ms_per_step": total_ms_step, "share_of_step": total_ms_step / (ms_image / STEPS_PER_IMAGE),
+            "method": "CUDA events around a CUDA graph of the step's launches of each shape, rotating buffers (> L2)",
+            "shapes": detail,
+            "groupnorm": {"bound": "hbm", "achieved": gn_b / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0,
+                          "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "launches": len(gn), "ms_per_image": gn_ms,
+                          "method": "eager in-model CUDA events (includes launch gaps for the small tensors)"}}
+    roof["groupnorm"]["frac"] = roof["groupnorm"]["achieved"] / roof["groupnorm"]["peak"]
+    return roof
+
+
+def step_times(pipe, cfg, reps=8):
+    """ms of ONE UNet call of each kind through the captured graphs (or eager when graphs are off): synchronous (counter 0)
+    and steady-state asynchronous (counter warmup+2), max over ranks.  Every rank replays the same sequence, so the peers'
+    flags always arrive."""
+    import torch
+    from torch import distributed as dist
+    unet = pipe.pipeline.unet
+    si = pipe.static_inputs
+    out = {}
+    for name, counter in (("sync", 0), ("async", cfg.warmup_steps + 2)):
+        def call():
+            unet.set_counter(counter)
+            unet(si["sample"], si["timestep"], si["encoder_hidden_states"], added_cond_kwargs=si.get("added_cond_kwargs"),
+                 return_dict=False)
+        unet.set_counter(0)
+        for c in range(cfg.warmup_steps + 3):             # bring the epoch clock into the state this kind of step expects
+            unet(si["sample"], si["timestep"], si["encoder_hidden_states"], added_cond_kwargs=si.get("added_cond_kwargs"),
+                 return_dict=False)
+        for _ in range(2):
+            call()
+        if cfg.world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=cfg.device)
+        if cfg.world_size > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        out[name] = ms.item()
+    return out
+
+
+def run_ours(a):
+    import torch
+    from torch import distributed as dist
+    from distrifuser_b200 import _lib
+    _lib.lib()
+    assert torch.cuda.is_available(), "bench.py (ours) needs a GPU"
+    R = a.resolution
+    cfg, pipe = build_pipe(a, R)
+    rank, world = cfg.rank, cfg.world_size
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE is {world} (launch with torch.distributed.run)"
+    dev = cfg.device
+    io = make_inputs(a, pipe, dev, R)
+
+    def make_image(pipe_, io_):
+        def image(host: bool):
+            kw = dict(num_inference_steps=STEPS_PER_IMAGE, guidance_scale=5.0, output_type="latent")
+            if host:
+                r = pipe_(prompt_embeds=io_["embeds_h"], pooled_prompt_embeds=io_["pooled_h"], latents=io_["lat_h"], **kw)
+                io_["out_h"].copy_(r.images, non_blocking=True)
+            else:
+                r = pipe_(prompt_embeds=io_["embeds_d"], pooled_prompt_embeds=io_["pooled_d"], latents=io_["lat_d"], **kw)
+            return r
+        return image
+    image = make_image(pipe, io)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, host: bool, k: int):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(k):
-            image(host)
+            fn(host)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -197,137 +458,107 @@ def run_ours(a):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(max(a.warmup, 3)):
+    warm = max(a.warmup, 3)
+    for _ in range(warm):
         image(False)
     sampler = ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
     n0 = _lib.LAUNCHES["total"]
-    total_ms = timed(False, a.steps)
+    total_ms = timed(image, False, a.steps)
     launches = _lib.LAUNCHES["total"] - n0
-    e2e_ms = timed(True, a.steps)
+    e2e_ms = timed(image, True, a.steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_image = total_ms / a.steps
     ms_image_e2e = e2e_ms / a.steps
 
-    # ---- exposed communication: same kernels with every publication / peer wait removed after warm-up
-    #      (mode "no_sync" = compute-only lower bound); (t(mode) - t(no_sync)) / t(mode)
+    # ---- exposed communication (SURVEY 8d): same kernels with every publication / peer wait removed after warm-up
+    #      (mode "no_sync" = compute-only lower bound); whole image and split by step kind
     exposed = None
     if world > 1 and cfg.n_device_per_batch > 1 and not a.no_exposed_comm and a.mode != "no_sync":
+        st_mode = step_times(pipe, cfg)
         pipe.set_mode("no_sync")
         for _ in range(2):
             image(False)
-        nosync_ms = timed(False, a.steps) / a.steps
+        nosync_ms = timed(image, False, max(2, min(a.steps, 5))) / max(2, min(a.steps, 5))
+        st_nosync = step_times(pipe, cfg)
         pipe.set_mode(a.mode)
         image(False)
+        base = st_nosync["async"]                   # a step of pure compute (no publication, no peer wait, local GroupNorm)
+        n_sync, n_async = cfg.warmup_steps + 1, STEPS_PER_IMAGE - cfg.warmup_steps - 1
+        ex_sync, ex_async = st_mode["sync"] - base, st_mode["async"] - base
         exposed = {"ms_image_no_sync": nosync_ms, "exposed_comm_pct": 100.0 * (ms_image - nosync_ms) / ms_image,
-                   "definition": "(t(mode) - t(no_sync)) / t(mode) over the whole 50-step image (5 synchronous + 45 asynchronous steps)"}
+                   "definition": "(t(mode) - t(no_sync)) / t(mode) over the whole 50-step image; no_sync keeps the 5 synchronous warm-up steps",
+                   "sync_step_ms": st_mode["sync"], "async_step_ms": st_mode["async"], "compute_only_step_ms": base,
+                   "exposed_ms_per_sync_step": ex_sync, "exposed_ms_per_async_step": ex_async,
+                   "exposed_pct_sync_step": 100.0 * ex_sync / st_mode["sync"], "exposed_pct_async_step": 100.0 * ex_async / st_mode["async"],
+                   "exposed_pct_image_from_steps": 100.0 * (n_sync * ex_sync + n_async * ex_async) / (n_sync * st_mode["sync"] + n_async * st_mode["async"]),
+                   "steps": {"sync": n_sync, "async": n_async},
+                   "method": "CUDA events around 8 replays of the captured graph of each step kind, max over ranks; compute-only = the "
+                             "steady-state step of mode no_sync (same kernels, no publication / peer waits, local GroupNorm statistics)"}
 
-    # ---- dominant-kernel roofline (fmha_fwd_kernel, self-attention launches).
-    #      (1) one instrumented eager image records the shape of every attention / GroupNorm launch of the model;
-    #      (2) every distinct self-attention shape is then timed with CUDA events as a CUDA graph of `count` back-to-back
-    #          launches on ROTATING buffers (total footprint > L2), i.e. the kernel's average launch duration at exactly the
-    #          step's shapes without the host-launch gaps that eager in-model events pick up for 30-us kernels.
-    cfg.use_cuda_graph_saved = cfg.use_cuda_graph
     roof = None
-    try:
-        cfg.use_cuda_graph = False
-        _lib.PROFILE = []
-        image(False)
-        torch.cuda.synchronize()
-        prof, _lib.PROFILE = _lib.PROFILE, None
-        cfg.use_cuda_graph = cfg.use_cuda_graph_saved
-        gn = [p for p in prof if p["kind"] == "gn"]
-        gn_ms = sum(p["start"].elapsed_time(p["end"]) for p in gn)
-        gn_b = sum(p["bytes"] for p in gn)
-        per_step = {}
-        for p in prof:
-            if p["kind"] == "self":
-                per_step[p["shape"]] = per_step.get(p["shape"], 0) + 1
-        per_step = {k: v // STEPS_PER_IMAGE for k, v in per_step.items()}          # launches of that shape per denoise step
-        import ctypes as C
-        L = _lib.lib()
-        seg = (C.c_int32 * 8)(*range(8))
-        total_ms_step, total_fl_step, detail = 0.0, 0.0, []
-        for (bb, lq_, lkv_, heads_, d_), count in per_step.items():
-            Cq = heads_ * d_
-            qs = [torch.randn(bb, lq_, Cq, device=dev, dtype=torch.float16) for _ in range(count)]
-            kvs = [torch.randn(bb, lkv_, 2 * Cq, device=dev, dtype=torch.float16) for _ in range(count)]
-            outs = [torch.empty_like(q_) for q_ in qs]
-            side = torch.cuda.Stream(device=dev)
+    if not a.no_roofline:
+        roof = attention_roofline(a, pipe, cfg, image, ms_image, dev, world, R)
 
-            def launch_all():
-                st = torch.cuda.current_stream().cuda_stream
-                for q_, kv_, o_ in zip(qs, kvs, outs):
-                    _lib.check(L.df_attn_fwd(_lib.null_comm(), q_.data_ptr(), kv_.data_ptr(), o_.data_ptr(), None, bb, lq_, lkv_,
-                                             heads_, d_, q_.stride(1), kv_.stride(1), o_.stride(1), 1, 0, seg, 0, 0, 0.0, None, 0,
-                                             st), "df_attn_fwd")
-            with torch.cuda.stream(side):
-                launch_all()
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                launch_all()
-            for _ in range(2):
-                g.replay()
-            reps = 5
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                g.replay()
-            e1.record()
-            torch.cuda.synchronize()
-            ms_launch = e0.elapsed_time(e1) / reps / count
-            fl = 4.0 * bb * lq_ * lkv_ * Cq
-            total_ms_step += ms_launch * count
-            total_fl_step += fl * count
-            detail.append({"shape": {"b": bb, "lq": lq_, "lkv": lkv_, "heads": heads_, "d": d_}, "launches_per_step": count,
-                           "avg_launch_ms": ms_launch, "tflops": fl / ms_launch / 1e9,
-                           "footprint_mb": count * (2 * bb * lq_ * Cq + bb * lkv_ * 2 * Cq) * 2 / 1e6})
-            del qs, kvs, outs, g
-        peaks = {}
+    # ---- hires: the north-star configuration (3840x3840) at the same N, one timed image after prepare()'s warm-up calls
+    hires = None
+    if not a.no_hires and a.hires_resolution != R and a.model == "sdxl":
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = peaks.get("bf16_tflops_sustained", 1590.0 * 1395.4 / 1700.9)
-        ach = total_fl_step / (total_ms_step * 1e-3) / 1e12 if total_ms_step > 0 else 0.0
-        n_launch = sum(per_step.values())
-        roof = {"kernel": "fmha_fwd_kernel (self-attention launches of one denoise step)", "bound": "tensor", "achieved": ach,
-                "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                # dram__bytes_read+write of ONE level-1 launch (b=2, Lq=Lkv=4096, 10 heads) from the ncu --set full capture in
-                # profiles/r1_fmha_lvl1.txt; its algorithmic bytes are 2*b*(2*Lq*C + 2*Lkv*C) = 41.9 MB (the O write stays in L2)
-                "traffic": 33.8e6 if (a.model == "sdxl" and R == 1024 and world == 1) else None,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback",
-                "launches_per_step": n_launch, "avg_launch_ms": total_ms_step / max(n_launch, 1),
-                "ms_per_step": total_ms_step, "share_of_step": total_ms_step / (ms_image / STEPS_PER_IMAGE),
-                "method": "CUDA events around a CUDA graph of the step's launches of each shape, rotating buffers (> L2)",
-                "shapes": detail,
-                "groupnorm": {"bound": "hbm", "achieved": gn_b / (gn_ms * 1e-3) / 1e9 if gn_ms > 0 else 0.0,
-                              "peak": peaks.get("hbm_gbs", 6650.0), "unit": "GB/s", "launches": len(gn), "ms_per_image": gn_ms,
-                              "method": "eager in-model CUDA events (includes launch gaps for the small tensors)"}}
-        roof["groupnorm"]["frac"] = roof["groupnorm"]["achieved"] / roof["groupnorm"]["peak"]
-    finally:
-        cfg.use_cuda_graph = cfg.use_cuda_graph_saved
-        _lib.PROFILE = None
+            if getattr(pipe, "comm_manager", None) is not None:
+                barrier()
+                pipe.comm_manager.close()
+            del pipe, image
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            HR = a.hires_resolution
+            t0 = time.perf_counter()
+            cfg_h, pipe_h = build_pipe(a, HR)
+            io_h = make_inputs(a, pipe_h, dev, HR)
+            image_h = make_image(pipe_h, io_h)
+            n_img = 1 if world == 1 else 2
+            if world > 1:
+                image_h(False)                       # one un-timed image: the first NVLink stores of every slot
+            hms = timed(image_h, False, n_img) / n_img
+            hires = {"resolution": HR, "ms_per_image": hms, "ms_per_denoise_step": hms / STEPS_PER_IMAGE, "images_timed": n_img,
+                     "parallelism": f"cfg{2 if (world > 1 and cfg_h.split_batch) else 1} x patch{cfg_h.n_device_per_batch}",
+                     "setup_s": None, "workload": f"SDXL UNet {HR}x{HR}, 50-step Euler, CFG batch 2 (BASELINE.json configs[3] image size)"}
+            if world > 1 and cfg_h.n_device_per_batch > 1 and not a.no_exposed_comm:
+                st_h = step_times(pipe_h, cfg_h, reps=3)
+                pipe_h.set_mode("no_sync")
+                st_hn = step_times(pipe_h, cfg_h, reps=3)
+                base = st_hn["async"]
+                n_sync, n_async = cfg_h.warmup_steps + 1, STEPS_PER_IMAGE - cfg_h.warmup_steps - 1
+                hires["exposed_comm"] = {
+                    "sync_step_ms": st_h["sync"], "async_step_ms": st_h["async"], "compute_only_step_ms": base,
+                    "exposed_pct_sync_step": 100.0 * (st_h["sync"] - base) / st_h["sync"],
+                    "exposed_pct_async_step": 100.0 * (st_h["async"] - base) / st_h["async"],
+                    "exposed_pct_image_from_steps": 100.0 * (n_sync * (st_h["sync"] - base) + n_async * (st_h["async"] - base)) /
+                                                    (n_sync * st_h["sync"] + n_async * st_h["async"])}
+            hires["setup_s"] = time.perf_counter() - t0 - hms * n_img / 1e3
+            if getattr(pipe_h, "comm_manager", None) is not None:
+                barrier()
+                pipe_h.comm_manager.close()
+        except Exception as e:                         # the headline line must survive a hires failure (e.g. out of memory)
+            hires = {"resolution": a.hires_resolution, "error": f"{type(e).__name__}: {e}"[:300]}
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:        # reported at N=1 only (rank 0's host cores)
-        v, threads, sample, _ = cpu_reference_sample(a.model, R, 1, 1)
-        cpu = {"value": v, "unit": "ms/image", "cores": threads, "kind": "port", "sample": sample}
+        r = cpu_reference_samples(a.model, R, 1, 1, 90.0)
+        cpu = {"value": r["ms_image"], "unit": "ms/image", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:
         n, b = cfg.n_device_per_batch, (1 if (cfg.do_classifier_free_guidance and cfg.split_batch and world > 1) else 2)
-        h2d = embeds_h.numel() * 2 + (pooled_h.numel() * 2 if pooled_h is not None else 0) + lat_h.numel() * 4
-        line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        h2d = io["embeds_h"].numel() * 2 + (io["pooled_h"].numel() * 2 if io["pooled_h"] is not None else 0) + io["lat_h"].numel() * 4
+        line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_image, "ms_per_denoise_step": ms_image / STEPS_PER_IMAGE, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": f"{a.model.upper()} UNet {R}x{R}, 50-step Euler, CFG batch 2, random-init weights",
                            "parallelism": f"cfg{2 if b == 1 else 1} x patch{n}", "mode": cfg.mode, "warmup_steps": cfg.warmup_steps,
                            "cuda_graph": cfg.use_cuda_graph, "l2": "working set (5.1 GB of weights per step) exceeds the 126 MB L2; no explicit flush"},
-                "roofline": roof, "cpu_baseline": cpu, "exposed_comm": exposed,
-                "e2e": {"value": ms_image_e2e, "unit": "ms/image", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_h.numel() * 4},
+                "roofline": roof, "cpu_baseline": cpu, "exposed_comm": exposed, "hires": hires,
+                "e2e": {"value": ms_image_e2e, "unit": "ms/image", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": io["out_h"].numel() * 4},
                 "gpu_launches": launches, "clocks": clocks}
         print_json(json.dumps(line))
     if world > 1:
@@ -352,6 +583,8 @@ def main():
     print_json = emit
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-gpu":
+        run_reference_gpu(a)
     else:
         run_ours(a)
 

@@ -24,7 +24,8 @@ EXPORTS = (
 
 class DfComm(C.Structure):
     _fields_ = [("base", C.c_void_p * MAX_WORLD), ("flags", C.c_void_p * MAX_WORLD), ("clock", C.c_void_p),
-                ("tickets", C.c_void_p), ("bank_stride", C.c_uint64), ("world", C.c_int32), ("rank", C.c_int32)]
+                ("tickets", C.c_void_p), ("bank_stride", C.c_uint64), ("spin_timeout_ns", C.c_uint64), ("world", C.c_int32),
+                ("rank", C.c_int32)]
 
 
 _lib = None

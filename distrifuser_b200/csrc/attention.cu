@@ -16,8 +16,7 @@
 //   warp 8     TMA producer: Q once, then K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
 //   warp 9     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
 //              issued as soon as the softmax warps have pulled S_j into registers (s_free), i.e. under their exp work
-// TMEM columns: S [0,128) O [128,192) P [192,256)   (fp32 S/O, packed fp16 P)
-#include <stdlib.h>
+// TMEM columns: S [0,128) P [128,192) O [192, 192 + 64*NBLK)   (fp32 S/O, packed fp16 P)
 
 #include "tc_ptx.cuh"
 
@@ -131,7 +130,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const void* map = &tm_kv_own;
         if (seg != own_seg) {
           const int r = segs.rank[seg];
-          if ((t == 0 || j == 0) && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
+          if ((t == 0 || j == 0) && wait_flags) {
+            spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd, comm.spin_timeout_ns);
+            // the acquire above is a generic-proxy read; the peers' rows are fetched next through the async proxy (TMA)
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+          }
           map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
         }
         const int ks = j % KSTAGES, vs = j % VSTAGES;
@@ -338,286 +341,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 
-// =====================================================================================================================
-// fmha2: two Q tiles per CTA (FA4-style pipeline), one CTA per SM, d <= 64.
-//
-// The profile of fmha_fwd_kernel (profiles/r1_fmha_v2_3840.txt) shows a per-tile LATENCY bound: ~3000 cycles per 128x128 tile
-// even for a CTA alone on its SM (s_full wait, tcgen05.ld, max chain, half-row exchange, MUFU section, tcgen05.st, arrive).
-// This kernel amortises that chain: a CTA owns 256 query rows = tiles A and B, one softmax warpgroup per tile with one thread
-// per full 128-column row (no half-row exchange, 204 registers available), K/V tiles are loaded once for both Q tiles, and the
-// MUFU-heavy exponential sections of the two warpgroups are forced to ALTERNATE with a pair of named barriers, so that each
-// group's serial part (waits, TMEM traffic, max) runs under the other group's exponentials.
-//   warps 0-3  softmax A    warps 4-7  softmax B    warp 8  TMA producer    warp 9  MMA issuer
-// TMEM (512 columns): S_A [0,128) S_B [128,256) P_A [256,320) P_B [320,384) O_A [384,448) O_B [448,512)
-constexpr int K2_KST = 3, K2_VST = 2;
-struct __align__(1024) Smem2 {
-  __half q[2][BM * HB];
-  __half k[K2_KST][BN * HB];
-  __half v[K2_VST][BN * HB];
-  uint64_t q_full;
-  uint64_t k_full[K2_KST], k_empty[K2_KST], v_full[K2_VST], v_empty[K2_VST];
-  uint64_t s_full[2], s_free[2], p_full[2], pv_done[2];
-  uint32_t tmem_base;
-};
-#ifndef DF_FMHA2_DEFAULT
-#define DF_FMHA2_DEFAULT 0   // flipped to 1 once fmha2 is validated and faster on the GPU (tools/sweep_attn.sh)
-#endif
-#ifndef DF2_EMU_PAIRS_OF_8
-#define DF2_EMU_PAIRS_OF_8 2
-#endif
-#ifndef DF2_ORDER_EXP
-#define DF2_ORDER_EXP 1
-#endif
-#ifndef DF2_SETMAXNREG
-#define DF2_SETMAXNREG 0     // 12 warps (2 idle): the softmax warpgroups grow to 208 registers, the TMA/MMA warpgroup shrinks to 80
-#endif
-constexpr int NTHREADS2 = DF2_SETMAXNREG ? 384 : NTHREADS;
-
-__global__ void __launch_bounds__(NTHREADS2, 1)
-fmha2_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
-                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
-                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
-                 float scale_log2) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  Smem2& sm = *reinterpret_cast<Smem2*>(smem_raw);
-  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * BM), head = blockIdx.y, bat = blockIdx.z;
-  const int tps = (lseg + BN - 1) / BN;
-  const int T = nseg * tps;
-
-  if (warp == WARP_MMA && lane == 0) {
-    mbar_init(&sm.q_full, 1);
-    for (int s = 0; s < K2_KST; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1); }
-    for (int s = 0; s < K2_VST; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1); }
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(&sm.s_full[x], 1); mbar_init(&sm.s_free[x], 4); mbar_init(&sm.p_full[x], 4); mbar_init(&sm.pv_done[x], 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == WARP_TMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = sm.tmem_base;
-
-#if DF2_SETMAXNREG
-  if (warp < NSOFTMAX_WARPS) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;" ::: "memory");
-  else asm volatile("setmaxnreg.dec.sync.aligned.u32 80;" ::: "memory");
-#endif
-  if (warp == WARP_TMA) {
-    // =============================================================== TMA producer
-    if (lane == 0) {
-      prefetch_tmap(&tm_q);
-      prefetch_tmap(&tm_kv_own);
-      mbar_expect_tx(&sm.q_full, 2 * BLK_BYTES);
-      tma_load_4d(sm.q[0], &tm_q, &sm.q_full, 0, head, q0, bat);
-      tma_load_4d(sm.q[1], &tm_q, &sm.q_full, 0, head, q0 + BM, bat);      // rows past lq are zero-filled
-      uint32_t rd = 0;
-      if (nseg > 1) rd = comm.clock[1];
-      int so = 0, t = 0;
-      for (int j = 0; j < T; ++j, ++t) {
-        if (t == tps) { t = 0; ++so; }
-        int seg = own_seg + so;
-        if (seg >= nseg) seg -= nseg;
-        const void* map = &tm_kv_own;
-        if (seg != own_seg) {
-          const int r = segs.rank[seg];
-          if (t == 0 && wait_flags) spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd);
-          map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
-        }
-        const int ks = j % K2_KST, vs = j % K2_VST;
-        mbar_wait(&sm.k_empty[ks], ((uint32_t)(j / K2_KST) & 1u) ^ 1u);
-        mbar_expect_tx(&sm.k_full[ks], BLK_BYTES);
-        tma_load_4d(sm.k[ks], map, &sm.k_full[ks], 0, head, t * BN, bat);
-        mbar_wait(&sm.v_empty[vs], ((uint32_t)(j / K2_VST) & 1u) ^ 1u);
-        mbar_expect_tx(&sm.v_full[vs], BLK_BYTES);
-        tma_load_4d(sm.v[vs], map, &sm.v_full[vs], 0, heads + head, t * BN, bat);
-      }
-    }
-  } else if (warp == WARP_MMA) {
-    // =============================================================== MMA issuer (single thread, both Q tiles)
-    if (lane == 0) {
-      auto qk = [&](int x, int j) {               // S_x = Q_x K_j^T
-        const uint32_t q_addr = smem_u32(sm.q[x]), k_addr = smem_u32(sm.k[j % K2_KST]);
-#pragma unroll
-        for (int kk = 0; kk < HB / 16; ++kk)
-          mma_ss(tmem + x * 128, smem_desc(q_addr + kk * 32, 16, 1024), smem_desc(k_addr + kk * 32, 16, 1024), IDESC_S, kk > 0);
-        tc_commit(&sm.s_full[x]);
-      };
-      auto pv = [&](int x, int j) {               // O_x += P_x V_j
-        const uint32_t v_addr = smem_u32(sm.v[j % K2_VST]);
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)
-          mma_ts(tmem + 384 + x * 64, tmem + 256 + x * 64 + kk * 8, smem_desc(v_addr + kk * 2048, 16384, 1024), IDESC_PV,
-                 (j > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&sm.pv_done[x]);
-      };
-      mbar_wait(&sm.q_full, 0);
-      mbar_wait(&sm.k_full[0], 0);
-      tc_fence_after();
-      qk(0, 0);
-      qk(1, 0);
-      tc_commit(&sm.k_empty[0]);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          const int ks = (j + 1) % K2_KST;
-          mbar_wait(&sm.k_full[ks], (uint32_t)((j + 1) / K2_KST) & 1u);
-          mbar_wait(&sm.s_free[0], (uint32_t)j & 1u);
-          tc_fence_after();
-          qk(0, j + 1);
-          mbar_wait(&sm.s_free[1], (uint32_t)j & 1u);
-          tc_fence_after();
-          qk(1, j + 1);
-          tc_commit(&sm.k_empty[ks]);
-        }
-        const int vs = j % K2_VST;
-        mbar_wait(&sm.v_full[vs], (uint32_t)(j / K2_VST) & 1u);
-        mbar_wait(&sm.p_full[0], (uint32_t)j & 1u);
-        tc_fence_after();
-        pv(0, j);
-        mbar_wait(&sm.p_full[1], (uint32_t)j & 1u);
-        tc_fence_after();
-        pv(1, j);
-        tc_commit(&sm.v_empty[vs]);
-      }
-    }
-  } else if (warp < NSOFTMAX_WARPS) {
-    // =============================================================== softmax warpgroup x (0 = tile A, 1 = tile B)
-    const int x = warp >> 2, quad = warp & 3;
-    const int row = quad * 32 + lane;                              // TMEM lane and row inside the tile
-    const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
-    const uint32_t col_s = x * 128, col_p = 256 + x * 64, col_o = 384 + x * 64;
-    float m_ref = -INFINITY, l = 0.f;
-#if DF2_ORDER_EXP
-    if (x == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // group A takes the first exponential section
-#endif
-    int t = 0;
-    for (int j = 0; j < T; ++j, ++t) {
-      if (t == tps) t = 0;
-      const int valid = min(BN, lseg - t * BN);
-      mbar_wait(&sm.s_full[x], (uint32_t)j & 1u);
-      tc_fence_after();
-      uint32_t sr[BN];
-      tmem_ld32(lane_base + col_s + 0, sr + 0);
-      tmem_ld32(lane_base + col_s + 32, sr + 32);
-      tmem_ld32(lane_base + col_s + 64, sr + 64);
-      tmem_ld32(lane_base + col_s + 96, sr + 96);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.s_free[x]);
-      if (valid < BN) {
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int c = 0; c < BN; ++c)
-          if (c >= valid) sr[c] = 0xff800000u;
-      }
-      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < BN; c += 8) {
-        mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
-        mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-        mx2 = max3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-        mx3 = max3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-      }
-      const float m_new = max3(max3(mx0, mx1, mx2), mx3, m_ref);
-      float alpha = 1.f;
-      bool moved = false;
-      if ((m_new - m_ref) * scale_log2 > 8.f) {
-        alpha = ex2((m_ref - m_new) * scale_log2);
-        m_ref = m_new;
-        l *= alpha;
-        moved = true;
-      }
-      const float neg_ref = -m_ref * scale_log2;
-      const uint64_t scale2 = pack2(scale_log2, scale_log2), negref2 = pack2(neg_ref, neg_ref);
-      uint32_t pr[BN / 2];
-      uint64_t sum2 = pack2(0.f, 0.f), sum2b = pack2(0.f, 0.f);
-#if DF2_ORDER_EXP
-      asm volatile("bar.sync %0, 256;" ::"r"(2 + x) : "memory");    // my turn on the MUFU pipe
-#endif
-#pragma unroll
-      for (int pi = 0; pi < BN / 2; ++pi) {
-        const uint64_t x2 = fma2(pack2(__uint_as_float(sr[2 * pi]), __uint_as_float(sr[2 * pi + 1])), scale2, negref2);
-        float p0, p1;
-        if ((pi & 7) < DF2_EMU_PAIRS_OF_8) {
-          ex2_poly2(x2, p0, p1);
-        } else {
-          float x0, x1;
-          unpack2(x2, x0, x1);
-          p0 = ex2(x0);
-          p1 = ex2(x1);
-        }
-        if (pi & 1) sum2b = add2(sum2b, pack2(p0, p1));
-        else sum2 = add2(sum2, pack2(p0, p1));
-        pr[pi] = pack_h2(p0, p1);
-      }
-#if DF2_ORDER_EXP
-      if (!(x == 1 && j == T - 1)) asm volatile("bar.arrive %0, 256;" ::"r"(3 - x) : "memory");   // hand the pipe to the other group
-#endif
-      float sum0, sum1;
-      unpack2(add2(sum2, sum2b), sum0, sum1);
-      l += sum0 + sum1;
-      if (j > 0) {
-        mbar_wait(&sm.pv_done[x], (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-        if (__any_sync(0xffffffffu, moved)) {
-#pragma unroll
-          for (int cb = 0; cb < 2; ++cb) {
-            uint32_t o[32];
-            tmem_ld32(lane_base + col_o + cb * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st32(lane_base + col_o + cb * 32, o);
-          }
-        }
-      }
-      tmem_st32(lane_base + col_p, pr);
-      tmem_st32(lane_base + col_p + 32, pr + 32);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.p_full[x]);
-    }
-    // ---- epilogue
-    mbar_wait(&sm.pv_done[x], (uint32_t)(T - 1) & 1u);
-    tc_fence_after();
-    const float inv_l = 1.f / l;
-    const int grow = q0 + x * BM + row;
-#pragma unroll
-    for (int cb = 0; cb < 2; ++cb) {
-      uint32_t o[32];
-      tmem_ld32(lane_base + col_o + cb * 32, o);
-      tmem_wait_ld();
-      if (grow < lq) {
-        __half* dst = out + ((int64_t)bat * lq + grow) * o_pitch + (int64_t)head * d + cb * 32;
-        const int nvec = (d - cb * 32) / 8;
-#pragma unroll
-        for (int vq = 0; vq < 4; ++vq) {
-          if (vq < nvec) {
-            int4 w;
-            w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
-            w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
-            w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
-            w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
-            st_v4(dst + vq * 8, w);
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == WARP_TMA) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-  }
-}
-
 // Combine the split-KV partials: out = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max_s m_s) * scale_log2).
 // One warp per (batch, head, q-row); lanes stride over the head columns.
 __global__ void __launch_bounds__(256) fmha_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
@@ -776,24 +499,7 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
         tq, tkv, (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg, own_seg, idx,      \
         wait_flags, sc, splits, part_o, part_ml);                                                                            \
   }
-  // Kernel choice: fmha2 (two Q tiles per CTA) when its grid still fills the SMs; DF_FMHA_FORCE=1|2 overrides (tests / A-B).
-  const char* force_env = getenv("DF_FMHA_FORCE");
-  const int force = force_env ? atoi(force_env) : 0;
-  static int sm_count = 0;
-  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
-  const long long grid2 = (long long)((lq + 2 * BM - 1) / (2 * BM)) * heads * b;
-  const bool use2 = nblk == 1 && splits == 1 && (force == 2 || (DF_FMHA2_DEFAULT && force == 0 && lq > BM && grid2 >= sm_count));
-  if (use2) {
-    static bool attr2 = false;
-    if (!attr2) {
-      DF_CHECK_CUDA(cudaFuncSetAttribute(fmha2_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem2)));
-      attr2 = true;
-    }
-    dim3 g2((lq + 2 * BM - 1) / (2 * BM), heads, b);
-    fmha2_fwd_kernel<<<g2, NTHREADS2, sizeof(Smem2), (cudaStream_t)stream>>>(tq, tkv, (const CUtensorMap*)kvmaps, comm, segs,
-                                                                           (__half*)out, lq, lseg, heads, d, o_pitch, nseg,
-                                                                           own_seg, idx, wait_flags, sc);
-  } else if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
+  if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA
   DF_CHECK_LAUNCH();
   if (splits > 1) {

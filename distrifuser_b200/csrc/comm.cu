@@ -19,7 +19,7 @@ void set_error(const char* fmt, ...) {
 using namespace df;
 
 extern "C" const char* df_last_error(void) { return df::g_err; }
-extern "C" int df_version(void) { return 1; }
+extern "C" int df_version(void) { return 2; }
 extern "C" int df_device_sm_count(int* out) {
   int dev = 0;
   DF_CHECK_CUDA(cudaGetDevice(&dev));
@@ -155,7 +155,7 @@ extern "C" int df_slot_publish(df_comm_t comm, const void* src, uint64_t rows, u
 __global__ void wait_kernel(df_comm_t c, int idx, uint32_t src_mask) {
   const uint32_t want = c.clock[1];
   int s = threadIdx.x;
-  if (s < c.world && (src_mask >> s & 1)) spin_until(c.flags[c.rank] + (size_t)idx * c.world + s, want);
+  if (s < c.world && (src_mask >> s & 1)) spin_until(c.flags[c.rank] + (size_t)idx * c.world + s, want, c.spin_timeout_ns);
 }
 extern "C" int df_slot_wait(df_comm_t comm, int idx, uint32_t src_mask, void* stream) {
   if (src_mask == 0) return 0;
@@ -191,7 +191,7 @@ template <typename V>
 __global__ void __launch_bounds__(256) out_collect_kernel(df_comm_t c, V* __restrict__ out, int64_t total_vec, int idx,
                                                           uint64_t tensor_off) {
   const uint32_t epoch = c.clock[2];
-  if (threadIdx.x < c.world) spin_until(c.flags[c.rank] + (size_t)idx * c.world + threadIdx.x, epoch);
+  if (threadIdx.x < c.world) spin_until(c.flags[c.rank] + (size_t)idx * c.world + threadIdx.x, epoch, c.spin_timeout_ns);
   __syncthreads();
   const V* src = (const V*)slot_ptr(c, c.rank, epoch, tensor_off, 0, 0);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x)

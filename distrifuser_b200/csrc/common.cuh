@@ -55,13 +55,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #ifndef DF_SPIN_TIMEOUT_NS
 #define DF_SPIN_TIMEOUT_NS 30000000000ull  // a peer that never arrives becomes a CUDA error, not a hung GPU
 #endif
-__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t want) {
+__device__ __forceinline__ void spin_until(const uint32_t* flag, uint32_t want, uint64_t timeout_ns = 0) {
   if (epoch_reached(ld_acquire_sys(flag), want)) return;
+  if (timeout_ns == 0) timeout_ns = DF_SPIN_TIMEOUT_NS;
   const uint64_t t0 = globaltimer_ns();
   uint32_t polls = 0;
   while (!epoch_reached(ld_acquire_sys(flag), want)) {
     __nanosleep(64);
-    if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > DF_SPIN_TIMEOUT_NS) {
+    if ((++polls & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
       printf("distrifuser_b200: timeout waiting for flag %p (have %u, want %u)\n", (const void*)flag, ld_volatile_u32(flag), want);
       __trap();
     }

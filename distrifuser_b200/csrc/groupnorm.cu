@@ -144,16 +144,16 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
   const int tid = threadIdx.x, nthr = blockDim.x;
   // parallel reduction of the per-CTA partials: `tpp` threads per (sample, group) pair, then a shared-memory fold
   __shared__ float2 red[512];
-  const int tpp = max(1, min(nthr / bG, 8));
-  if (tid < bG * tpp) {
-    const int i = tid / tpp, r = tid - i * tpp;
+  const int tpp = max(1, min(nthr / bG, 8));      // bG * tpp <= 512 (host guard: bG <= 512)
+  for (int e = tid; e < bG * tpp; e += nthr) {    // stride loop: bG may exceed the block (b*groups = 512 on 320 threads)
+    const int i = e / tpp, r = e - i * tpp;
     const int b = i / G, g = i - b * G;
     float s = 0.f, ss = 0.f;
     for (int k = r; k < nchunk; k += tpp) {
       float2 p = partial[((size_t)b * nchunk + k) * G + g];
       s += p.x; ss += p.y;
     }
-    red[tid] = make_float2(s, ss);
+    red[e] = make_float2(s, ss);
   }
   __syncthreads();
   for (int i = tid; i < bG; i += nthr) {
@@ -178,7 +178,7 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
     if (tid < c.world && (group_mask >> tid & 1)) st_release_sys(c.flags[tid] + (size_t)idx * c.world + c.rank, pub);
   };
   auto wait_all = [&]() {
-    if (tid < c.world && (group_mask >> tid & 1)) spin_until(c.flags[c.rank] + (size_t)idx * c.world + tid, rd);
+    if (tid < c.world && (group_mask >> tid & 1)) spin_until(c.flags[c.rank] + (size_t)idx * c.world + tid, rd, c.spin_timeout_ns);
     __syncthreads();
   };
 

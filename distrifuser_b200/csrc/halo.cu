@@ -51,8 +51,8 @@ __global__ void __launch_bounds__(256) halo_assemble_kernel(df_comm_t c, const c
                                                             uint64_t slot_bytes, int up_rank, int down_rank, int wait_flags) {
   const uint32_t rd = (up_rank >= 0 || down_rank >= 0) ? c.clock[1] : 0u;
   if (wait_flags) {
-    if (threadIdx.x == 0 && up_rank >= 0) spin_until(c.flags[c.rank] + (size_t)idx * c.world + up_rank, rd);
-    if (threadIdx.x == 1 && down_rank >= 0) spin_until(c.flags[c.rank] + (size_t)idx * c.world + down_rank, rd);
+    if (threadIdx.x == 0 && up_rank >= 0) spin_until(c.flags[c.rank] + (size_t)idx * c.world + up_rank, rd, c.spin_timeout_ns);
+    if (threadIdx.x == 1 && down_rank >= 0) spin_until(c.flags[c.rank] + (size_t)idx * c.world + down_rank, rd, c.spin_timeout_ns);
     __syncthreads();
   }
   const uint64_t row_bytes = row_vec * 16;

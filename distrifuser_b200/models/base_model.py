@@ -1,14 +1,24 @@
-"""Reference: distrifuser/models/base_model.py:8-52 (same attributes and methods; ModelMixin/ConfigMixin are
-diffusers types and only matter for from_pretrained, so a plain nn.Module is used when diffusers is absent)."""
+"""Reference: distrifuser/models/base_model.py:8-52 (same attributes and methods).
+
+The reference derives BaseModel from diffusers' (ModelMixin, ConfigMixin): StableDiffusion(XL)Pipeline.from_pretrained(...,
+unet=DistriUNetPP) type-checks the component against ModelMixin.  When diffusers is importable the same bases are used
+here; without it (this image) a plain nn.Module carries the `dtype` / `device` properties the mixin would provide."""
+import torch
 from torch import nn
 
 from ..modules.base_module import BaseModule
 from ..utils import DistriConfig, PatchParallelismCommManager
 
+try:  # pragma: no cover - depends on the environment
+    from diffusers import ConfigMixin, ModelMixin
+    _BASES = (ModelMixin, ConfigMixin)
+except Exception:
+    _BASES = (nn.Module,)
 
-class BaseModel(nn.Module):
+
+class BaseModel(*_BASES):
     def __init__(self, model: nn.Module, distri_config: DistriConfig):
-        super().__init__()
+        super(BaseModel, self).__init__()
         self.model = model
         self.distri_config = distri_config
         self.comm_manager = None
@@ -48,3 +58,16 @@ class BaseModel(nn.Module):
     def synchronize(self):                                         # base_model.py:47-52
         if self.comm_manager is not None:
             self.comm_manager.join()
+
+
+def _first_param(m: nn.Module):
+    for p in m.parameters():
+        return p
+    for b in m.buffers():
+        return b
+    return None
+
+
+if not any(hasattr(b, "dtype") for b in _BASES):                   # ModelMixin.dtype / .device for the nn.Module fallback
+    BaseModel.dtype = property(lambda self: getattr(_first_param(self), "dtype", torch.float32))
+    BaseModel.device = property(lambda self: getattr(_first_param(self), "device", torch.device("cpu")))

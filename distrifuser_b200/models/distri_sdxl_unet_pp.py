@@ -12,7 +12,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from ..modules.base_module import BaseModule
+from ..modules.base_module import BaseModule, nvtx_range
 from ..modules.pp.attn import DistriCrossAttentionPP, DistriSelfAttentionPP
 from ..modules.pp.conv2d import DistriConv2dPP
 from ..modules.pp.groupnorm import DistriGroupNorm
@@ -68,6 +68,7 @@ class DistriUNetPP(BaseModel):  # for Patch Parallelism
             return 0
         return 2 if cfg.mode == "no_sync" else 1
 
+    @nvtx_range("DistriUNetPP")
     def forward(
         self,
         sample: torch.FloatTensor,

@@ -1,8 +1,40 @@
 """Reference: distrifuser/modules/base_module.py:6-29 (same attributes and state protocol)."""
+import functools
+import os
+
 import torch
 from torch import nn
 
 from ..utils import DistriConfig
+
+NVTX = os.environ.get("DF_NVTX", "1") != "0"     # NVTX range per wrapper call (SURVEY 5 tracing row); DF_NVTX=0 removes them
+
+
+_HAS_CUDA = None
+
+
+def nvtx_range(name: str):
+    """Decorator: brackets a wrapper's forward with an NVTX range `name[idx]` when CUDA is in use (shows up in nsys / ncu
+    --nvtx; a no-op on captured-graph replays, where Python does not run)."""
+    def deco(fn):
+        if not NVTX:
+            return fn
+
+        @functools.wraps(fn)
+        def wrapped(self, *args, **kwargs):
+            global _HAS_CUDA
+            if _HAS_CUDA is None:
+                _HAS_CUDA = torch.cuda.is_available()
+            if not _HAS_CUDA:
+                return fn(self, *args, **kwargs)
+            idx = getattr(self, "idx", None)
+            torch.cuda.nvtx.range_push(name if idx is None else f"{name}[{idx}]")
+            try:
+                return fn(self, *args, **kwargs)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
 
 
 class BaseModule(nn.Module):

@@ -12,7 +12,7 @@ from torch.nn import functional as F
 
 from ... import _lib
 from ...utils import DistriConfig
-from ..base_module import BaseModule
+from ..base_module import BaseModule, nvtx_range
 
 
 class DistriAttentionPP(BaseModule):
@@ -84,6 +84,7 @@ class DistriCrossAttentionPP(DistriAttentionPP):
         super().__init__(module, distri_config)
         self.kv_cache = None
 
+    @nvtx_range("DistriCrossAttentionPP")
     def forward(self, hidden_states, encoder_hidden_states=None, scale: float = 1.0, *args, **kwargs):
         assert encoder_hidden_states is not None                         # attn.py:55
         self._require_cuda_half(hidden_states, "DistriCrossAttentionPP")
@@ -107,18 +108,29 @@ class DistriSelfAttentionPP(DistriAttentionPP):
         super().__init__(module, distri_config)
         # q and k|v read the same activations: one [C -> 3C] GEMM instead of two launches (to_kv is kept: it is the reference's
         # attribute, attn.py:39, and sizes the registered slot)
-        to_q = module.to_q
         self._w_qkv = None
-        if isinstance(to_q, nn.Linear) and to_q.bias is None and self.to_kv.bias is None and \
-                to_q.in_features == self.to_kv.in_features and to_q.out_features * 2 == self.to_kv.out_features:
-            self._w_qkv = torch.cat([to_q.weight.data, self.to_kv.weight.data], 0).contiguous()
+        self._w_qkv_key = None
 
-    def _apply(self, fn, recurse=True):
-        super()._apply(fn, recurse)
-        if self._w_qkv is not None:
-            self._w_qkv = fn(self._w_qkv)          # plain tensor: follows .to() / .half() of the module
-        return self
+    def _qkv_weight(self, dtype):
+        """[to_q.weight ; to_kv.weight] as one [3C, C] matrix, rebuilt whenever either source changed (load_state_dict,
+        LoRA fuse/unfuse, in-place edits, .to()/.half()): the key holds the tensors' version counters and storage."""
+        to_q, to_kv = self.module.to_q, self.to_kv
+        if not (isinstance(to_q, nn.Linear) and to_q.bias is None and to_kv.bias is None and
+                to_q.in_features == to_kv.in_features and to_q.out_features * 2 == to_kv.out_features and
+                to_q.weight.dtype == dtype and to_kv.weight.dtype == dtype):
+            return None
+        wq, wkv = to_q.weight, to_kv.weight
+        key = (wq._version, wkv._version, wq.data_ptr(), wkv.data_ptr(), wq.device, dtype)
+        if key != self._w_qkv_key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("DistriSelfAttentionPP: attention weights changed since the last eager call; run one "
+                                   "eager UNet call (pipeline.prepare()) before capturing CUDA graphs")
+            with torch.no_grad():
+                self._w_qkv = torch.cat([wq.detach(), wkv.detach()], 0).contiguous()
+            self._w_qkv_key = key
+        return self._w_qkv
 
+    @nvtx_range("DistriSelfAttentionPP")
     def forward(self, hidden_states, encoder_hidden_states=None, scale: float = 1.0, *args, **kwargs):
         cfg = self.distri_config
         self._require_cuda_half(hidden_states, "DistriSelfAttentionPP")
@@ -128,8 +140,9 @@ class DistriSelfAttentionPP(DistriAttentionPP):
         cm = self.comm_manager
         if n > 1 and self._recording() and self.idx is None:
             self.idx = cm.register_tensor((b, l, self.to_kv.out_features), hidden_states.dtype, layer_type="attn")  # :185-190
-        if self._w_qkv is not None and self._w_qkv.dtype == hidden_states.dtype:
-            qkv = F.linear(hidden_states, self._w_qkv)                   # attn.py:121,125 in one GEMM
+        w_qkv = self._qkv_weight(hidden_states.dtype)
+        if w_qkv is not None:
+            qkv = F.linear(hidden_states, w_qkv)                         # attn.py:121,125 in one GEMM
             q, kv = qkv[..., :c], qkv[..., c:]                           # views: row pitch 3C, no copies
         else:
             q = attn.to_q(hidden_states)                                 # attn.py:121

@@ -10,7 +10,7 @@ from torch.nn import functional as F
 
 from ... import _lib
 from ...utils import DistriConfig
-from ..base_module import BaseModule
+from ..base_module import BaseModule, nvtx_range
 
 
 class DistriConv2dPP(BaseModule):
@@ -33,6 +33,7 @@ class DistriConv2dPP(BaseModule):
         xs = F.pad(x[:, :, max(lo, 0):min(hi, h), :], [padding, padding, pad_t, pad_b])
         return F.conv2d(xs, self.module.weight, self.module.bias, stride=stride, padding="valid")
 
+    @nvtx_range("DistriConv2dPP")
     def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
         cfg = self.distri_config
         n = cfg.n_device_per_batch

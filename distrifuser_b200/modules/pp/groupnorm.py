@@ -9,7 +9,7 @@ from torch import nn
 
 from ... import _lib
 from ...utils import DistriConfig
-from ..base_module import BaseModule
+from ..base_module import BaseModule, nvtx_range
 
 MODE_LOCAL, MODE_SYNC, MODE_CORRECTED, MODE_STALE = 0, 1, 2, 3
 
@@ -38,6 +38,7 @@ class DistriGroupNorm(BaseModule):
             return (MODE_SYNC if self._bound() else MODE_LOCAL), 1, 0      # groupnorm.py:74-91
         return MODE_LOCAL, 0, 0                                      # groupnorm.py:92-93 (stock nn.GroupNorm)
 
+    @nvtx_range("DistriGroupNorm")
     def forward(self, x: torch.Tensor, addend: torch.Tensor | None = None) -> torch.Tensor:
         """`addend` ([b, C], optional) is added to every pixel before the norm: GroupNorm(x + addend[:, :, None, None])."""
         module = self.module

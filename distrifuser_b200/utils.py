@@ -50,6 +50,9 @@ class DistriConfig:
         else:
             rank, world_size = 0, 1                                     # utils.py:44-47 (single GPU)
         assert is_power_of_2(world_size)                                # utils.py:49
+        assert world_size <= _lib.MAX_WORLD, (
+            f"distrifuser_b200 shards one image over the GPUs of ONE NVSwitch box (<= {_lib.MAX_WORLD} ranks, "
+            f"DF_MAX_WORLD); got world_size={world_size}")
         assert mode in ("corrected_async_gn", "stale_gn", "sync_gn", "separate_gn", "full_sync", "no_sync")
         if parallelism != "patch":
             raise NotImplementedError(
@@ -254,14 +257,23 @@ class PatchParallelismCommManager:
             g.flags[i] = self._peer_ptrs[r] + self._flags_group_off
         g.clock, g.tickets = self.clock.data_ptr(), self._tickets.data_ptr()
         g.bank_stride, g.world, g.rank = bank_stride, n, cfg.split_idx()
+        # device-side flag waits trap (CUDA error instead of a hung GPU) after this long; raise it when a rank may stall for
+        # a long time inside a step (cudnn.benchmark autotune in the eager pre-run, ncu / compute-sanitizer serialisation)
+        timeout_ns = int(float(os.environ.get("DF_SPIN_TIMEOUT_S", "0")) * 1e9)
+        g.spin_timeout_ns = timeout_ns
         w = DfComm()
         for r in range(world):
             w.base[r] = self._peer_ptrs[r]
             w.flags[r] = self._peer_ptrs[r] + self._flags_world_off
         w.clock, w.tickets = self.clock.data_ptr(), self._tickets.data_ptr() + 4 * nt   # world ticket after the group's
         w.bank_stride, w.world, w.rank = bank_stride, world, cfg.rank
+        w.spin_timeout_ns = timeout_ns
         self.group, self.world, self.bank_stride = g, w, bank_stride
         self.comm_stream = torch.cuda.Stream(device=cfg.device, priority=-1)
+        import atexit
+        import weakref
+        ref = weakref.ref(self)
+        atexit.register(lambda: ref() is not None and ref().close())
         self.handles = [None for _ in range(nt)]
         self.buffer_list = [self.arena for _ in range(n)]     # non-None marks "buffers created" (utils.py:160-163); views: get_buffer_list
         if world > 1:
@@ -284,6 +296,12 @@ class PatchParallelismCommManager:
         return out
 
     # ------------------------------------------------------------------ step protocol
+    # BANK-REUSE INVARIANT.  Bank e % 3 is overwritten by the peers' stores of epoch e+3 without any "consumed"
+    # acknowledgement.  That is safe only because every UNet call ends with df_output_gather, which makes each rank wait
+    # for the epsilon strip of EVERY world rank: no rank can start call t+1 before all ranks finished the kernels of call
+    # t, so ranks drift by < 1 call and a store of epoch e+3 can never meet a read of epoch e (reads of epoch e happen in
+    # calls e and e+1 only).  A path that skips the gather (e.g. returning the local strip) must add its own per-call
+    # world barrier, or stale K/V / halo rows get corrupted silently.
     def step_begin(self, kind: int):
         """kind 0 = synchronous, 1 = asynchronous, 2 = frozen (see df_step_begin)."""
         st = torch.cuda.current_stream().cuda_stream
@@ -346,8 +364,15 @@ class PatchParallelismCommManager:
         self.communicate()
         self.join()
 
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
     def close(self):
-        if self._arena_ptr is None:
+        """Unmaps the peers' arenas and frees this rank's (also run from __del__ and at interpreter exit)."""
+        if getattr(self, "_arena_ptr", None) is None:
             return
         L = _lib.lib()
         torch.cuda.synchronize(self.distri_config.device)

@@ -38,7 +38,7 @@ extern "C" {
 
 /* ---- errors / info ------------------------------------------------------------------------------ */
 const char* df_last_error(void);
-int df_version(void);                       /* ABI version, currently 1 */
+int df_version(void);                       /* ABI version, currently 2 */
 int df_device_sm_count(int* out);
 
 /* ---- symmetric memory: replaces the flat NCCL buffers of PatchParallelismCommManager.create_buffer
@@ -58,6 +58,7 @@ typedef struct {
   uint32_t* clock;                 /* this rank's epoch clock: [0]=publish, [1]=read, [2]=output epoch     */
   uint32_t* tickets;               /* this rank's per-tensor CTA ticket counters (local scratch, zeroed)   */
   uint64_t bank_stride;            /* bytes between banks                                                   */
+  uint64_t spin_timeout_ns;        /* device-side flag waits trap after this long (0 = default 30 s)       */
   int32_t world;                   /* members in this communicator                                          */
   int32_t rank;                    /* this rank's index in the communicator                                 */
 } df_comm_t;

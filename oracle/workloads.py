@@ -85,6 +85,8 @@ UNET_CASES = (
     UNetCase("sdxl_w2_sepgn", world_size=2, split_batch=False, mode="separate_gn"),
     UNetCase("sd15_w2_nosplit", family="tiny_sd15", world_size=2, split_batch=False, mode="stale_gn"),
     UNetCase("sdxl_w8_split", world_size=8),                          # n=4, b=1
+    UNetCase("sd15_w4_nosplit", family="tiny_sd15", world_size=4, split_batch=False, mode="stale_gn"),   # n=4, b=2; d=40/80/160
+    UNetCase("sd15_w8_split", family="tiny_sd15", world_size=8),      # n=4, b=1, corrected_async_gn (BASELINE configs[4] layout)
 )
 
 

@@ -38,7 +38,7 @@ def test_library_is_sm100a_tcgen05(libpath):
 def test_error_channel(libpath):
     from distrifuser_b200 import _lib
     L = _lib.lib()
-    assert L.df_version() == 1
+    assert L.df_version() == 2
     rc = L.df_step_begin(None, 7, None)          # argument validation happens before any CUDA call
     assert rc != 0 and b"df_step_begin" in L.df_last_error()
 
@@ -95,3 +95,14 @@ def test_rank_math_matches_reference():
                     assert c.batch_idx() == d.batch_idx() and c.split_idx() == d.split_idx()
                     grp = c.patch_group_ranks()
                     assert rank in grp and len(grp) == d.n_device_per_batch
+
+
+def test_base_model_derives_from_diffusers_mixins_when_importable():
+    """with diffusers importable BaseModel must be a (ModelMixin, ConfigMixin) like the reference's
+    (distrifuser/models/base_model.py:8), otherwise StableDiffusionXLPipeline.from_pretrained(unet=...) rejects it."""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "run_from_pretrained.py"), "check-bases"], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "OK bases" in r.stdout, r.stdout + r.stderr

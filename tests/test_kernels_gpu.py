@@ -44,12 +44,7 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (1, 130, 4100, 3, 64),         # split-KV with ragged q and k/v tiles
     (1, 100, 3000, 2, 40),         # split-KV, zero-padded head dim
 ])
-@pytest.mark.parametrize("kernel", [1, 2])
-def test_attention_single_segment(b, lq, lk, heads, d, kernel, monkeypatch):
-    """kernel 1 = fmha_fwd_kernel (one Q tile per CTA, two CTAs per SM); 2 = fmha2_fwd_kernel (two Q tiles per CTA)."""
-    if kernel == 2 and d > 64:
-        pytest.skip("fmha2 covers d <= 64")
-    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
+def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)
     Cq = heads * d
     q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16)
@@ -69,10 +64,8 @@ def test_attention_split_kv_is_planned_for_small_grids():
     assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
-def test_attention_large_logits_rescale(kernel, monkeypatch):
+def test_attention_large_logits_rescale():
     """Rows whose running max jumps by > 2^8 between tiles exercise the O-correction path."""
-    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
     torch.manual_seed(1)
     b, lq, lk, heads, d = 1, 128, 512, 1, 64
     q = torch.randn(b, lq, d, device="cuda", dtype=torch.float16) * 4
@@ -84,12 +77,10 @@ def test_attention_large_logits_rescale(kernel, monkeypatch):
     assert err < 4e-3, f"max abs err {err}"
 
 
-@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("n,own", [(2, 0), (2, 1), (4, 2)])
-def test_attention_multi_segment_stale_slots(n, own, kernel, monkeypatch):
+def test_attention_multi_segment_stale_slots(n, own):
     """K/V of the peers is read in place from the arena slots of the READ epoch (attn.py:136-138 without the cat)."""
     from distrifuser_b200 import _lib
-    monkeypatch.setenv("DF_FMHA_FORCE", str(kernel))
     torch.manual_seed(2)
     b, lseg, heads, d = 2, 200, 2, 64
     Cq = heads * d
@@ -110,6 +101,44 @@ def test_attention_multi_segment_stale_slots(n, own, kernel, monkeypatch):
     out = _attn(q, segs[own], heads, comm=arena.comm, maps=maps.data_ptr(), nseg=n, own=own, lseg=lseg, wait=1)
     full = torch.cat(segs, 1)
     ref = sdpa_ref(q, full[..., :Cq], full[..., Cq:], heads)
+    err = (out.float() - ref).abs().max().item()
+    arena.close()
+    assert err < 2e-3, f"max abs err {err}"
+
+
+def _sdpa_ref_chunked(q, k, v, heads, chunk=1800):
+    """fp32 reference for shapes whose [heads, lq, lk] score tensor does not fit: q rows in chunks."""
+    out = torch.empty(q.shape, dtype=torch.float32, device=q.device)
+    for r0 in range(0, q.shape[1], chunk):
+        out[:, r0:r0 + chunk] = sdpa_ref(q[:, r0:r0 + chunk], k, v, heads)
+    return out
+
+
+@pytest.mark.parametrize("lq,lseg,heads,own", [(3600, 3600, 20, 1),      # SDXL 3840^2, n=4, level 2 (Lkv 14 400)
+                                               (14400, 14400, 10, 3)])   # SDXL 3840^2, n=4, level 1 (Lkv 57 600)
+def test_attention_3840_shapes_four_ragged_segments(lq, lseg, heads, own):
+    """BASELINE configs[3] per-rank shapes: 4 segments whose last tile is ragged (3600 = 28*128 + 16,
+    14400 = 112*128 + 64), peers read in place from the arena bank of the read epoch, against a chunked fp32 reference."""
+    from distrifuser_b200 import _lib
+    torch.manual_seed(11)
+    n, b, d = 4, 1, 64
+    Cq = heads * d
+    nbytes = b * lseg * 2 * Cq * 2
+    arena = LoopbackArena(n, [nbytes], rank=own)
+    epoch = 4
+    segs = [torch.randn(b, lseg, 2 * Cq, device="cuda", dtype=torch.float16) for _ in range(n)]
+    for s in range(n):
+        if s != own:
+            arena.slot(epoch, 0, s, nbytes).copy_(segs[s].flatten())
+            arena.flags[0, s] = epoch
+    arena.set_clock(pub=epoch + 1, rd=epoch)
+    maps = torch.empty(_lib.NBANKS * n * _lib.TENSORMAP_BYTES, dtype=torch.uint8, device="cuda")
+    _lib.check(_lib.lib().df_attn_make_kvmaps(arena.comm, arena.tensor_off[0], arena.slot_bytes[0], b, lseg, heads, d,
+                                              maps.data_ptr(), torch.cuda.current_stream().cuda_stream), "kvmaps")
+    q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16)
+    out = _attn(q, segs[own], heads, comm=arena.comm, maps=maps.data_ptr(), nseg=n, own=own, lseg=lseg, wait=1)
+    full = torch.cat(segs, 1)
+    ref = _sdpa_ref_chunked(q, full[..., :Cq], full[..., Cq:], heads)
     err = (out.float() - ref).abs().max().item()
     arena.close()
     assert err < 2e-3, f"max abs err {err}"

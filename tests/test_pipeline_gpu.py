@@ -19,7 +19,8 @@ def _psnr(a, b):
     return 10 * torch.log10(b.abs().max() ** 2 / max(mse, 1e-20)).item()
 
 
-@pytest.mark.parametrize("name,graph", [("sdxl_w1", True), ("sdxl_w2_nosplit", True)])
+@pytest.mark.parametrize("name,graph", [("sdxl_w1", True), ("sdxl_w2_nosplit", True),
+                                        ("sd15_w2_nosplit", True)])     # SD1.x: DistriSDPipeline.__call__, DDIM scheduler
 def test_trajectory_matches_oracle(name, graph):
     case = dataclasses.replace({c.name: c for c in workloads.UNET_CASES}[name], warmup_steps=2)
     want = harness.run_trajectory(case, num_steps=6)
@@ -30,3 +31,16 @@ def test_trajectory_matches_oracle(name, graph):
         assert torch.equal(lat, got[0]), "every rank must hold the same latents"
         p = _psnr(lat, want)
         assert p > 35.0, f"{name} rank{r}: PSNR {p:.1f} dB vs the fp32 oracle trajectory"
+
+
+@pytest.mark.parametrize("family", ["sdxl", "sd15"])
+def test_from_pretrained_with_diffusers_type_check(family):
+    """Distri{SDXL,SD}Pipeline.from_pretrained (pipelines.py:20-42,179-200) against a `diffusers` whose pipeline
+    constructor type-checks `unet=` against ModelMixin (as the real package does): BaseModel must derive from the mixins."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, "run_from_pretrained.py"), family], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "OK from_pretrained" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]

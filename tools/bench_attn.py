@@ -24,11 +24,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--no-split", action="store_true", help="disable split-KV (A/B)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 fmha_fwd_kernel, 2 fmha2_fwd_kernel")
     a = ap.parse_args()
     from distrifuser_b200 import _lib
-    if a.kernel:
-        os.environ["DF_FMHA_FORCE"] = str(a.kernel)
     L = _lib.lib()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     for name in a.shapes.split(","):

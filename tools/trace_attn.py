@@ -9,7 +9,6 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from distrifuser_b200 import _lib  # noqa: E402
 
-os.environ["DF_FMHA_FORCE"] = "1"
 L = _lib.lib()
 b, lq, lk, h, d = (int(x) for x in (sys.argv[1:6] or (1, 3600, 14400, 20, 64)))
 q = torch.randn(b, lq, h * d, device="cuda", dtype=torch.float16)

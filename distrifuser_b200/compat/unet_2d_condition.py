@@ -65,12 +65,32 @@ class GEGLU(nn.Module):
     def __init__(self, dim_in, dim_out):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
+        self._fused = None            # (key, interleaved weight, interleaved bias) of the one-kernel projection + gate
+        self.norm_fused = None        # set by BasicTransformerBlock: LayerNorm whose output feeds this projection (unused here)
+
+    def _fused_weights(self):
+        """Interleaved copy of proj.weight / proj.bias for the fused tcgen05 GEMM + GEGLU epilogue (ops.linear_geglu); rebuilt
+        when the source tensors change (load_state_dict, .to(), in-place edits)."""
+        from .. import ops
+        w, b = self.proj.weight, self.proj.bias
+        key = (w._version, w.data_ptr(), w.dtype, w.device, None if b is None else (b._version, b.data_ptr()))
+        if self._fused is None or self._fused[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("GEGLU: weights changed since the last eager call; run one eager UNet call before capturing graphs")
+            with torch.no_grad():
+                wi, bi = ops.geglu_interleave(w.detach(), None if b is None else b.detach())
+            self._fused = (key, wi, bi)
+        return self._fused[1], self._fused[2]
 
     def forward(self, x):
+        if x.is_cuda and x.dtype == torch.float16:
+            from .. import ops
+            D, K = self.proj.out_features // 2, self.proj.in_features
+            if ops.use_fused_linear("geglu") and D % ops.GEGLU_BLOCK == 0 and ops.linear_supported(x.numel() // K, 2 * D, K, geglu=True):
+                wi, bi = self._fused_weights()
+                return ops.linear_geglu(x, wi, bi)          # projection + gate in ONE kernel: the [.., 8C] tensor never exists
+            return ops.geglu(self.proj(x))                  # library GEMM + one fused gate kernel
         y = self.proj(x)
-        if y.is_cuda and y.dtype == torch.float16:
-            from ..ops import geglu
-            return geglu(y)                      # one fused kernel instead of gelu + mul
         x, gate = y.chunk(2, dim=-1)
         return x * F.gelu(gate)
 

@@ -41,7 +41,8 @@ struct __align__(1024) SmemT {
   __half k[KSTAGES][NBLK][BN * HB];
   __half v[VSTAGES][NBLK][BN * HB];
   float red_max[2][2][BM];   // [tile parity][column half][row]: partial row maxima exchanged between the two half-row warps
-  float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue
+  float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue (v3: [0][row] = row sum)
+  float red_ref[BM];         // v3: exponent reference of every row for the epilogue / split-KV partials
   uint64_t q_full;
   uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
   uint64_t s_full;
@@ -58,6 +59,13 @@ template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; sta
 struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
 };
+
+#ifndef DF_FMHA_V3
+#define DF_FMHA_V3 1         // 1: one warp per 16 full rows, 16x256b fragments + quad shuffles; 0: v2 half-row warps + smem exchange
+#endif
+#ifndef DF_EMU_QUARTERS
+#define DF_EMU_QUARTERS 1    // v3: of every 4 column groups, this many take the polynomial exp2 (FMA/ALU pipes) instead of MUFU
+#endif
 
 #ifdef DF_TRACE
 // cycle-level event trace of CTA (0,0,0) for kernel tuning (tools/trace_attn.py); compiled out by default
@@ -195,6 +203,171 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // =============================================================== softmax / correction / epilogue (warps 0-7)
+#if DF_FMHA_V3
+    // Warp w owns 16 rows (TMEM lanes 32*(w&3) + 16*(w>>2) ..+15) and ALL 128 S columns of them, in the 16x256b fragment
+    // layout: thread t holds rows rA = t/4 and rB = t/4 + 8, columns 8i + 2(t%4) + {0,1} for i = 0..15 (64 values).  A row
+    // lives in one quad, so the row maximum is two shuffles -- no shared-memory exchange and no named barrier between warps
+    // (v2 split rows over two warps and paid an STS + 64-thread bar.sync + LDS per tile).
+    const int quad = warp & 3, hr = warp >> 2;
+    const uint32_t lane16 = (uint32_t)(quad * 32 + hr * 16);
+    const uint32_t lane_base = tmem + (lane16 << 16);
+    const int c4 = lane & 3, r8 = lane >> 2;
+    float m_refA = -INFINITY, m_refB = -INFINITY;                  // exponent references of rows rA / rB (raw S units)
+    float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
+    int t = j_begin % tps;
+    for (int j = 0; j < T; ++j, ++t) {
+      if (t == tps) t = 0;
+      const int valid = min(BN, lseg - t * BN);
+      mbar_wait(&sm.s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      if (threadIdx.x == 0) DF_TR(0, j);
+      uint32_t sr[64];
+      tmem_ld_16x256b_x16(lane_base + COL_S, sr);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
+      if (threadIdx.x == 0) DF_TR(1, j);
+      if (valid < BN) {                              // ragged last tile of a segment only (warp-uniform branch)
+        asm volatile("" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            if (8 * i + 2 * c4 + k >= valid) { sr[4 * i + k] = 0xff800000u; sr[4 * i + 2 + k] = 0xff800000u; }
+      }
+      float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        mA0 = max3(mA0, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
+        mB0 = max3(mB0, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
+        mA1 = max3(mA1, __uint_as_float(sr[4 * i + 4]), __uint_as_float(sr[4 * i + 5]));
+        mB1 = max3(mB1, __uint_as_float(sr[4 * i + 6]), __uint_as_float(sr[4 * i + 7]));
+      }
+      float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+      if (threadIdx.x == 0) DF_TR(2, j);
+      // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
+      float alphaA = 1.f, alphaB = 1.f;
+      bool moved = false;
+      if ((mA - m_refA) * scale_log2 > 8.f) { alphaA = ex2((m_refA - mA) * scale_log2); m_refA = mA; lA *= alphaA; moved = true; }
+      if ((mB - m_refB) * scale_log2 > 8.f) { alphaB = ex2((m_refB - mB) * scale_log2); m_refB = mB; lB *= alphaB; moved = true; }
+      const float nA = -m_refA * scale_log2, nB = -m_refB * scale_log2;
+      const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
+      uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
+      // two halves of 32 packed P columns each: the first half is stored while the second is still being exponentiated
+      // (keeps 16 instead of 32 P registers live under the 96-register cap of two CTAs per SM)
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t pr[16];
+#pragma unroll
+        for (int ii = 0; ii < 8; ++ii) {
+          const int i = hf * 8 + ii;
+          const uint64_t xA = fma2(pack2(__uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1])), scale2, nA2);
+          const uint64_t xB = fma2(pack2(__uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3])), scale2, nB2);
+          float a0, a1, b0, b1;
+          if ((i & 3) < DF_EMU_QUARTERS) {             // this share of the exponentials runs on the FMA / ALU pipes
+            ex2_poly2(xA, a0, a1);
+            ex2_poly2(xB, b0, b1);
+          } else {
+            float x0, x1;
+            unpack2(xA, x0, x1); a0 = ex2(x0); a1 = ex2(x1);
+            unpack2(xB, x0, x1); b0 = ex2(x0); b1 = ex2(x1);
+          }
+          sA = add2(sA, pack2(a0, a1));
+          sB = add2(sB, pack2(b0, b1));
+          pr[2 * ii] = pack_h2(a0, a1);
+          pr[2 * ii + 1] = pack_h2(b0, b1);
+        }
+        if (hf == 0) {
+          if (threadIdx.x == 0) DF_TR(3, j);
+          if (j > 0) {
+            mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
+            tc_fence_after();
+            if (threadIdx.x == 0) DF_TR(4, j);
+            if (__any_sync(0xffffffffu, moved)) {            // rare: rescale this warp's 16 rows of O
+#pragma unroll
+              for (int blk = 0; blk < NBLK; ++blk) {
+                uint32_t o[32];
+                tmem_ld_16x256b_x8(lane_base + COL_O + blk * HB, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int i2 = 0; i2 < 8; ++i2) {
+                  o[4 * i2] = __float_as_uint(__uint_as_float(o[4 * i2]) * alphaA);
+                  o[4 * i2 + 1] = __float_as_uint(__uint_as_float(o[4 * i2 + 1]) * alphaA);
+                  o[4 * i2 + 2] = __float_as_uint(__uint_as_float(o[4 * i2 + 2]) * alphaB);
+                  o[4 * i2 + 3] = __float_as_uint(__uint_as_float(o[4 * i2 + 3]) * alphaB);
+                }
+                tmem_st_16x256b_x8(lane_base + COL_O + blk * HB, o);
+              }
+            }
+          }
+        }
+        tmem_st_16x128b_x8(lane_base + COL_P + hf * 32, pr);
+      }
+      {
+        float s0, s1;
+        unpack2(sA, s0, s1); lA += s0 + s1;
+        unpack2(sB, s0, s1); lB += s0 + s1;
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.p_full);
+      if (threadIdx.x == 0) DF_TR(5, j);
+    }
+    // ---- epilogue: row sums / references -> shared memory (quad reduce), then O / l -> fp16 -> HBM in the 32x32b layout
+    //      (thread = row, 16-byte stores): warp w writes columns [32*(w>>2), +32) of the 32 rows of its lane quarter
+    lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
+    lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
+    if (c4 == 0) {
+      sm.red_sum[0][lane16 + r8] = lA; sm.red_sum[0][lane16 + r8 + 8] = lB;
+      sm.red_ref[lane16 + r8] = m_refA; sm.red_ref[lane16 + r8 + 8] = m_refB;
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const int half = hr;
+    const int row = quad * 32 + lane;
+    const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
+    const float l_row = sm.red_sum[0][row];
+    const float m_ref = sm.red_ref[row];
+    const float inv_l = 1.f / l_row;
+    mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
+    tc_fence_after();
+    const int64_t prow = (((int64_t)split * gridDim.z / kv_splits + bat) * heads + head) * lq + q0 + row;   // partial-result row
+    if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk) {
+      uint32_t o[32];
+      const int col0 = blk * HB + half * 32;        // first head column of this chunk
+      tmem_ld32(row_base + COL_O + col0, o);
+      tmem_wait_ld();
+      if (q0 + row < lq) {
+        if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
+          float* dst = part_o + prow * (NBLK * HB) + col0;
+#pragma unroll
+          for (int vq = 0; vq < 8; ++vq)
+            st_v4(dst + vq * 4, make_int4((int)o[vq * 4], (int)o[vq * 4 + 1], (int)o[vq * 4 + 2], (int)o[vq * 4 + 3]));
+        } else {
+          __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
+          const int nvec = (d - col0) / 8;          // 16-byte vectors of real (un-padded) head columns in this chunk
+#pragma unroll
+          for (int vq = 0; vq < 4; ++vq) {
+            if (vq < nvec) {
+              int4 w;
+              w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
+              w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
+              w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
+              w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
+              st_v4(dst + vq * 8, w);
+            }
+          }
+        }
+      }
+    }
+#else
     const int quad = warp & 3, half = warp >> 2;                   // TMEM lane quarter, S column half
     const int row = quad * 32 + lane;                              // == TMEM lane
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
@@ -332,6 +505,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+#endif
   }
   tc_fence_before();
   __syncthreads();

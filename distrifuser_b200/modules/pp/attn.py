@@ -141,13 +141,25 @@ class DistriSelfAttentionPP(DistriAttentionPP):
         if n > 1 and self._recording() and self.idx is None:
             self.idx = cm.register_tensor((b, l, self.to_kv.out_features), hidden_states.dtype, layer_type="attn")  # :185-190
         w_qkv = self._qkv_weight(hidden_states.dtype)
+        live = n > 1 and self._bound()
+        sync = live and (cfg.mode == "full_sync" or self._is_sync_step())
+        ship = live and (sync or cfg.mode != "no_sync")                  # attn.py:133 / :139-140
+        published = False
         if w_qkv is not None:
-            qkv = F.linear(hidden_states, w_qkv)                         # attn.py:121,125 in one GEMM
+            from ... import ops
+            if ops.use_fused_linear("qkv") and ops.linear_supported(b * l, 3 * c, c):
+                # hand-written tcgen05 GEMM; its epilogue stores the k|v columns straight into the peers' arena slots and the
+                # last CTA stamps their flags: no enqueue copy (utils.py:187), no separate publication kernel
+                pub = (cm.group, c, self.idx, cm.peers_mask(), cm.tensor_off[self.idx], cm.slot_bytes[self.idx]) if ship else None
+                qkv = ops.linear(hidden_states, w_qkv, publish=pub)
+                published = ship
+            else:
+                qkv = F.linear(hidden_states, w_qkv)                     # attn.py:121,125 in one GEMM
             q, kv = qkv[..., :c], qkv[..., c:]                           # views: row pitch 3C, no copies
         else:
             q = attn.to_q(hidden_states)                                 # attn.py:121
             kv = self.to_kv(hidden_states)                               # attn.py:125
-        if n == 1 or not self._bound():
+        if not live:
             # attn.py:127-131: one rank, or buffers not created yet (n identical copies of kv give the same softmax)
             out = self._attend(q, kv, l, 1, 0, False)
         else:
@@ -157,11 +169,8 @@ class DistriSelfAttentionPP(DistriAttentionPP):
                 _lib.check(_lib.lib().df_attn_make_kvmaps(cm.group, cm.tensor_off[self.idx], cm.slot_bytes[self.idx], b, l,
                                                           heads, c // heads, self._kvmaps.data_ptr(),
                                                           torch.cuda.current_stream().cuda_stream), "df_attn_make_kvmaps")
-            sync = cfg.mode == "full_sync" or self._is_sync_step()
-            if sync:
-                cm.enqueue(self.idx, kv, async_stream=False)             # attn.py:133: everyone needs it this step
-            elif cfg.mode != "no_sync":
-                cm.enqueue(self.idx, kv, async_stream=True)              # attn.py:139-140: hidden under the attention
+            if ship and not published:
+                cm.enqueue(self.idx, kv, async_stream=not sync)          # sync: everyone needs it this step; async: hidden
             out = self._attend(q, kv, l, n, r, True)                     # attn.py:134-153, peers' segments in place
         out = self._project_out(out, hidden_states)
         self.counter += 1

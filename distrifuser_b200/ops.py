@@ -31,3 +31,75 @@ def add_layernorm(x: torch.Tensor, r: torch.Tensor | None, norm: torch.nn.LayerN
                                            norm.bias.data_ptr(), x.numel() // C, C, float(norm.eps),
                                            torch.cuda.current_stream().cuda_stream), "df_add_layernorm")
     return s, y
+
+
+# ---------------------------------------------------------------------------------------------------- tcgen05 GEMM (csrc/linear.cu)
+import os as _os
+
+# which Linear layers run on the hand-written GEMM: comma list out of {geglu, qkv, out, ff2, proj}; "all" / "none".
+# Default = the set measured faster than cuBLAS on B200 (tools/bench_linear.py, profiles/r2_linear_vs_cublas.txt).
+_FUSED_LINEAR = set(_os.environ.get("DF_LINEAR", "geglu").replace("all", "geglu,qkv,out,ff2,proj").split(","))
+
+
+def use_fused_linear(kind: str) -> bool:
+    return kind in _FUSED_LINEAR
+
+
+GEGLU_BLOCK = 128      # rows of the interleaved GEGLU weight: [hidden block t (128 rows) | gate block t (128 rows)] per 256-row tile
+
+
+def linear_supported(M: int, N: int, K: int, geglu: bool = False) -> bool:
+    return bool(_lib.lib().df_linear_supported(M, N, K, 1 if geglu else 0))
+
+
+def geglu_interleave(weight: torch.Tensor, bias: torch.Tensor | None):
+    """diffusers GEGLU.proj holds [hidden (D rows) ; gate (D rows)]; the fused kernel wants them interleaved in blocks of 128
+    so that one 256-column accumulator tile carries both halves of 128 outputs."""
+    two_d, K = weight.shape
+    D = two_d // 2
+    assert D % GEGLU_BLOCK == 0
+    w = torch.stack([weight[:D].reshape(D // GEGLU_BLOCK, GEGLU_BLOCK, K), weight[D:].reshape(D // GEGLU_BLOCK, GEGLU_BLOCK, K)], 1)
+    w = w.reshape(two_d, K).contiguous()
+    b = None
+    if bias is not None:
+        b = torch.stack([bias[:D].reshape(-1, GEGLU_BLOCK), bias[D:].reshape(-1, GEGLU_BLOCK)], 1).reshape(two_d).contiguous()
+    return w, b
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+           out: torch.Tensor | None = None, publish=None) -> torch.Tensor:
+    """x[..., K] @ weight[N, K]^T (+ bias) (+ residual) on the hand-written tcgen05 GEMM.  `publish` = (comm, pub_col0, idx,
+    peer_mask, tensor_off, slot_bytes): the columns >= pub_col0 also go into the peers' arena slots."""
+    assert x.is_cuda and x.dtype == torch.float16 and weight.dtype == torch.float16 and x.stride(-1) == 1 and weight.stride(-1) == 1
+    K = x.shape[-1]
+    N = weight.shape[0]
+    x2 = x.reshape(-1, K)
+    M = x2.shape[0]
+    if out is None:
+        out = torch.empty((*x.shape[:-1], N), dtype=x.dtype, device=x.device)
+    o2 = out.view(-1, N)
+    r2 = residual.reshape(-1, N) if residual is not None else None
+    if publish is not None:
+        comm, pub_col0, idx, mask, off, sb = publish
+    else:
+        comm, pub_col0, idx, mask, off, sb = _lib.null_comm(), 0, 0, 0, 0, 0
+    _lib.check(_lib.lib().df_linear_fwd(comm, x2.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        r2.data_ptr() if r2 is not None else None, o2.data_ptr(), M, N, K, x2.stride(0),
+                                        weight.stride(0), r2.stride(0) if r2 is not None else 0, o2.stride(0), 0,
+                                        int(publish is not None), pub_col0, idx, mask, off, sb, 0,
+                                        torch.cuda.current_stream().cuda_stream), "df_linear_fwd")
+    return out
+
+
+def linear_geglu(x: torch.Tensor, w_interleaved: torch.Tensor, b_interleaved: torch.Tensor | None) -> torch.Tensor:
+    """hidden * gelu_erf(gate) of the GEGLU projection in ONE kernel; weights from geglu_interleave()."""
+    assert x.is_cuda and x.dtype == torch.float16 and x.stride(-1) == 1
+    K = x.shape[-1]
+    N = w_interleaved.shape[0]
+    x2 = x.reshape(-1, K)
+    out = torch.empty((*x.shape[:-1], N // 2), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().df_linear_fwd(_lib.null_comm(), x2.data_ptr(), w_interleaved.data_ptr(),
+                                        b_interleaved.data_ptr() if b_interleaved is not None else None, None, out.data_ptr(),
+                                        x2.shape[0], N, K, x2.stride(0), w_interleaved.stride(0), 0, N // 2, 1, 0, 0, 0, 0, 0, 0, 0,
+                                        torch.cuda.current_stream().cuda_stream), "df_linear_fwd")
+    return out

@@ -104,7 +104,10 @@ def load_peaks() -> dict:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
-def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_warm: int, budget_s: float):
+FLOPS_STEP = {512: 3.18e12, 1024: 13.52e12, 2048: 71.82e12, 3840: 464.92e12}   # SDXL, per CFG-pair denoise step
+
+
+def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_warm: int, budget_s: float, sample_resolution=None):
     """Times the oracle port of the reference's CPU path (fp32, world_size 1: the stock UNet forward exactly as
     DistriUNetPP.forward runs it when nothing is wrapped, distri_sdxl_unet_pp.py:118-133) on ALL host cores, at the benched
     resolution.  One SAMPLE = one denoise step of ONE classifier-free-guidance branch (batch 1) of the full-size UNet; the
@@ -115,9 +118,20 @@ def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_war
     import torch
     from oracle import pp_modules, workloads
     t_begin = time.perf_counter()
-    threads = os.cpu_count() or 1
+    threads = int(os.environ.get("DF_CPU_THREADS", "0")) or (os.cpu_count() or 1)
     torch.set_num_threads(threads)                      # torchrun exports OMP_NUM_THREADS=1: do not inherit it silently
     family = "sdxl" if model == "sdxl" else "sd15"
+    target_resolution = resolution
+    scale, scale_note = 1.0, ""
+    if sample_resolution is not None and sample_resolution != resolution:
+        # bounded sample for the in-arm `cpu_baseline` key: the reference's own CPU-runnable case (BASELINE.json configs[0], 512^2),
+        # scaled to the benched image by the per-step FLOP ratio of SURVEY Appendix B
+        if model == "sdxl" and resolution in FLOPS_STEP and sample_resolution in FLOPS_STEP:
+            scale = FLOPS_STEP[resolution] / FLOPS_STEP[sample_resolution]
+        else:
+            scale = (resolution / sample_resolution) ** 2
+        scale_note = f"; sampled at {sample_resolution}x{sample_resolution} and scaled x{scale:.2f} (per-step FLOP ratio to {resolution}x{resolution})"
+        resolution = sample_resolution
     latent = resolution // 8
     unet = workloads.make_unet(family, 0)
     cfg = workloads.DuckConfig(1, 0, height=resolution, width=resolution, do_classifier_free_guidance=False)
@@ -133,21 +147,26 @@ def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_war
         return time.perf_counter() - t0
 
     with torch.no_grad():
-        for i in range(max(1, want_warm)):          # at least one warm-up sample; more only while they fit 40 % of the budget
-            if i > 0 and (time.perf_counter() - t_begin) + warm_t > 0.4 * budget_s:
-                break
-            warm_t = one()
-            warm_done += 1
+        first = one()
+        if first > 20.0 or first > 0.25 * budget_s:
+            times.append(first)                     # a sample this long is its own warm-up (allocation effects << 1 %): count it
+        else:
+            warm_done, warm_t = 1, first
+            for i in range(1, max(1, want_warm)):   # more warm-up samples only while they fit 40 % of the budget
+                if (time.perf_counter() - t_begin) + warm_t > 0.4 * budget_s:
+                    break
+                warm_t = one()
+                warm_done += 1
         while len(times) < max(1, want_timed):      # at least one timed sample; more only while the next one fits the budget
             if times and (time.perf_counter() - t_begin) + times[-1] > budget_s:
                 break
             times.append(one())
     sample_s = sum(times) / len(times)
-    ms_image = sample_s * 2 * STEPS_PER_IMAGE * 1e3
+    ms_image = sample_s * 2 * STEPS_PER_IMAGE * 1e3 * scale
     sample = (f"{len(times)} timed + {warm_done} warm-up samples; one sample = one denoise step of one CFG branch (batch 1, fp32) of "
               f"the full {family} UNet at {resolution}x{resolution} on {threads} host threads: {sample_s:.2f} s/sample "
               f"(min {min(times):.2f}, max {max(times):.2f}); ms/image = sample x 2 branches x {STEPS_PER_IMAGE} steps; "
-              f"model build {build_s:.0f} s outside the timed region")
+              f"model build {build_s:.0f} s outside the timed region{scale_note}")
     return dict(ms_image=ms_image, threads=threads, sample=sample, sample_s=sample_s, timed=len(times), warm=warm_done)
 
 
@@ -545,7 +564,7 @@ def run_ours(a):
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:        # reported at N=1 only (rank 0's host cores)
-        r = cpu_reference_samples(a.model, R, 1, 1, 90.0)
+        r = cpu_reference_samples(a.model, R, 1, 1, 60.0, sample_resolution=512)
         cpu = {"value": r["ms_image"], "unit": "ms/image", "cores": r["threads"], "kind": "port", "sample": r["sample"]}
 
     if rank == 0:

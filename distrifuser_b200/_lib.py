@@ -74,7 +74,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (bench.py reports the count of OUR launches inside the timed region)
-KERNELS_PER_CALL = {"df_groupnorm_fwd": 2, "df_attn_fwd": 1, "df_halo_push": 1, "df_halo_assemble": 1,
+KERNELS_PER_CALL = {"df_groupnorm_fwd": 1, "df_attn_fwd": 1, "df_halo_push": 1, "df_halo_assemble": 1,
                     "df_slot_publish": 1, "df_slot_wait": 1, "df_step_begin": 1, "df_output_gather": 2, "df_geglu": 1, "df_add_layernorm": 1,
                     "df_linear_fwd": 1}
 LAUNCHES = {"total": 0}

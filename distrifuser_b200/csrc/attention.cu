@@ -42,13 +42,14 @@ struct __align__(1024) SmemT {
   __half v[VSTAGES][NBLK][BN * HB];
   float red_max[2][2][BM];   // [tile parity][column half][row]: partial row maxima exchanged between the two half-row warps
   float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue (v3: [0][row] = row sum)
-  float red_ref[BM];         // v3: exponent reference of every row for the epilogue / split-KV partials
-  uint64_t q_full;
+  float red_ref[2][BM];      // v3: exponent reference of every row for the epilogue / split-KV partials ([unit parity][row])
+  uint64_t q_full, q_empty;   // Q tile of the current work unit loaded / no longer read by the tensor core
   uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
   uint64_t s_full;
   uint64_t s_free;
   uint64_t p_full;
   uint64_t pv_done;
+  uint64_t o_free;            // the epilogue of the previous work unit has pulled O out of TMEM
   uint32_t tmem_base;
 };
 template <int NBLK> struct Cfg;
@@ -85,7 +86,8 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<NBLK>::CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
-                float scale_log2, int kv_splits, float* __restrict__ part_o, float2* __restrict__ part_ml) {
+                float scale_log2, int kv_splits, int nbz /* batch * kv_splits */, float* __restrict__ part_o,
+                float2* __restrict__ part_ml) {
   constexpr int KSTAGES = Cfg<NBLK>::KST, VSTAGES = Cfg<NBLK>::VST;
   constexpr uint32_t TMEM_COLS = Cfg<NBLK>::TMEM, TILE_BYTES = NBLK * BLK_BYTES;
   using Smem = SmemT<NBLK, KSTAGES, VSTAGES>;
@@ -94,15 +96,28 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // split-KV (small grids: the K/V range of one (batch, head, q-tile) is shared by `kv_splits` CTAs, combined afterwards)
-  const int q0 = blockIdx.x * BM, head = blockIdx.y, bat = blockIdx.z / kv_splits, split = blockIdx.z % kv_splits;
+  // PERSISTENT CTAs: the grid is min(#work units, resident CTA slots); CTA c walks the units c, c + gridDim.x, ...  A work unit
+  // is one 128-row Q tile of one (batch, head) -- or, with split-KV (small grids), one K/V range of it.  The roles keep their
+  // rings / barrier phases running across units (tile counter g), so the TMEM allocation, barrier set-up, tensor-map fetch and
+  // pipeline fill are paid once per CTA and the K/V loads of the next unit run under the epilogue of the current one.
+  const int nqt = (lq + BM - 1) / BM;
   const int tps = (lseg + BN - 1) / BN;  // tiles per segment
   const int T_all = nseg * tps;
-  const int j_begin = (int)((long long)split * T_all / kv_splits);
-  const int T = (int)((long long)(split + 1) * T_all / kv_splits) - j_begin;   // tiles of this CTA (>= 1: kv_splits <= T_all)
+  const int n_units = nqt * heads * nbz;
+  auto decode = [&](int u, int& q0, int& head, int& bat, int& split, int& j_begin, int& T) {
+    const int qt = u % nqt, rest = u / nqt;
+    head = rest % heads;
+    const int z = rest / heads;
+    bat = z / kv_splits; split = z - bat * kv_splits;
+    q0 = qt * BM;
+    j_begin = (int)((long long)split * T_all / kv_splits);
+    T = (int)((long long)(split + 1) * T_all / kv_splits) - j_begin;   // >= 1: kv_splits <= T_all
+  };
 
   if (warp == WARP_MMA && lane == 0) {
     mbar_init(&sm.q_full, 1);
+    mbar_init(&sm.q_empty, 1);
+    mbar_init(&sm.o_free, NSOFTMAX_WARPS);
     for (int s = 0; s < KSTAGES; ++s) { mbar_init(&sm.k_full[s], 1); mbar_init(&sm.k_empty[s], 1); }
     for (int s = 0; s < VSTAGES; ++s) { mbar_init(&sm.v_full[s], 1); mbar_init(&sm.v_empty[s], 1); }
     mbar_init(&sm.s_full, 1);
@@ -125,44 +140,50 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (lane == 0) {
       prefetch_tmap(&tm_q);
       prefetch_tmap(&tm_kv_own);
-      mbar_expect_tx(&sm.q_full, TILE_BYTES);
-#pragma unroll
-      for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
-      int so = j_begin / tps, t = j_begin - so * tps;   // segment order index, tile inside the segment (one division, outside the loop)
-      for (int j = 0; j < T; ++j, ++t) {
-        if (t == tps) { t = 0; ++so; }
-        int seg = own_seg + so;
-        if (seg >= nseg) seg -= nseg;
-        const void* map = &tm_kv_own;
-        if (seg != own_seg) {
-          const int r = segs.rank[seg];
-          if ((t == 0 || j == 0) && wait_flags) {
-            spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd, comm.spin_timeout_ns);
-            // the acquire above is a generic-proxy read; the peers' rows are fetched next through the async proxy (TMA)
-            asm volatile("fence.proxy.async.global;" ::: "memory");
+      uint32_t g = 0, ui = 0;                              // K/V tiles and work units issued so far by this CTA
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+        int q0, head, bat, split, j_begin, T;
+        decode(u, q0, head, bat, split, j_begin, T);
+        mbar_wait(&sm.q_empty, (ui & 1u) ^ 1u);            // every Q K^T of the previous unit has completed
+        mbar_expect_tx(&sm.q_full, TILE_BYTES);
+#pragma unroll
+        for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
+        int so = j_begin / tps, t = j_begin - so * tps;   // segment order index, tile inside the segment (one division, outside the loop)
+        for (int j = 0; j < T; ++j, ++t, ++g) {
+          if (t == tps) { t = 0; ++so; }
+          int seg = own_seg + so;
+          if (seg >= nseg) seg -= nseg;
+          const void* map = &tm_kv_own;
+          if (seg != own_seg) {
+            const int r = segs.rank[seg];
+            if ((t == 0 || j == 0) && wait_flags) {
+              spin_until(comm.flags[comm.rank] + (size_t)idx * comm.world + r, rd, comm.spin_timeout_ns);
+              // the acquire above is a generic-proxy read; the peers' rows are fetched next through the async proxy (TMA)
+              asm volatile("fence.proxy.async.global;" ::: "memory");
+            }
+            map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
           }
-          map = kvmaps + (size_t)(rd % DF_NBANKS) * comm.world + r;
+          const uint32_t ks = g % KSTAGES, vs = g % VSTAGES;
+          mbar_wait(&sm.k_empty[ks], ((g / KSTAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.k[ks][blk], map, &sm.k_full[ks], blk * HB, head, t * BN, bat);
+          mbar_wait(&sm.v_empty[vs], ((g / VSTAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.v[vs][blk], map, &sm.v_full[vs], blk * HB, heads + head, t * BN, bat);
         }
-        const int ks = j % KSTAGES, vs = j % VSTAGES;
-        mbar_wait(&sm.k_empty[ks], ((uint32_t)(j / KSTAGES) & 1u) ^ 1u);
-        mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
-#pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.k[ks][blk], map, &sm.k_full[ks], blk * HB, head, t * BN, bat);
-        mbar_wait(&sm.v_empty[vs], ((uint32_t)(j / VSTAGES) & 1u) ^ 1u);
-        mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
-#pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.v[vs][blk], map, &sm.v_full[vs], blk * HB, heads + head, t * BN, bat);
       }
     }
   } else if (warp == WARP_MMA) {
     // =============================================================== MMA issuer (single thread)
     if (lane == 0) {
       const uint32_t q_addr = smem_u32(sm.q);
-      auto issue_qk = [&](int j) {
-        const int st = j % KSTAGES;
-        mbar_wait(&sm.k_full[st], (uint32_t)(j / KSTAGES) & 1u);
+      auto issue_qk = [&](uint32_t g) {
+        const uint32_t st = g % KSTAGES;
+        mbar_wait(&sm.k_full[st], (g / KSTAGES) & 1u);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sm.k[st]);
 #pragma unroll
@@ -174,31 +195,43 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(&sm.k_empty[st]);
         tc_commit(&sm.s_full);
       };
-      mbar_wait(&sm.q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) {
-          mbar_wait(&sm.s_free, (uint32_t)j & 1u);   // S_j is in the softmax warps' registers
+      uint32_t g = 0, ui = 0;                              // K/V tiles and work units consumed so far by this CTA
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+        int q0, head, bat, split, j_begin, T;
+        decode(u, q0, head, bat, split, j_begin, T);
+        mbar_wait(&sm.q_full, ui & 1u);
+        if (g > 0) {                                       // S still holds the last tile of the previous unit until the
+          mbar_wait(&sm.s_free, (g - 1) & 1u);             // softmax warps have pulled it into registers
           tc_fence_after();
-          DF_TR(8, j);
-          issue_qk(j + 1);
-          DF_TR(9, j);
         }
-        const int st = j % VSTAGES;
-        mbar_wait(&sm.p_full, (uint32_t)j & 1u);
-        mbar_wait(&sm.v_full[st], (uint32_t)(j / VSTAGES) & 1u);
-        tc_fence_after();
-        DF_TR(10, j);
-        const uint32_t v_addr = smem_u32(sm.v[st]);
+        issue_qk(g);
+        if (T == 1) tc_commit(&sm.q_empty);
+        for (int j = 0; j < T; ++j, ++g) {
+          if (j + 1 < T) {
+            mbar_wait(&sm.s_free, g & 1u);                 // S_j is in the softmax warps' registers
+            tc_fence_after();
+            DF_TR(8, g);
+            issue_qk(g + 1);
+            if (j + 2 == T) tc_commit(&sm.q_empty);        // last Q K^T of this unit: the Q tile may be overwritten once it completes
+            DF_TR(9, g);
+          }
+          const uint32_t st = g % VSTAGES;
+          mbar_wait(&sm.p_full, g & 1u);
+          mbar_wait(&sm.v_full[st], (g / VSTAGES) & 1u);
+          if (j == 0 && ui > 0) mbar_wait(&sm.o_free, (ui - 1) & 1u);   // previous unit's O has left TMEM
+          tc_fence_after();
+          DF_TR(10, g);
+          const uint32_t v_addr = smem_u32(sm.v[st]);
 #pragma unroll
-        for (int blk = 0; blk < NBLK; ++blk)
+          for (int blk = 0; blk < NBLK; ++blk)
 #pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk)
-            mma_ts(tmem + COL_O + blk * HB, tmem + COL_P + kk * 8, smem_desc(v_addr + blk * BLK_BYTES + kk * 2048, 16384, 1024),
-                   IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&sm.v_empty[st]);
-        tc_commit(&sm.pv_done);
-        DF_TR(11, j);
+            for (int kk = 0; kk < BN / 16; ++kk)
+              mma_ts(tmem + COL_O + blk * HB, tmem + COL_P + kk * 8, smem_desc(v_addr + blk * BLK_BYTES + kk * 2048, 16384, 1024),
+                     IDESC_PV, (j > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&sm.v_empty[st]);
+          tc_commit(&sm.pv_done);
+          DF_TR(11, g);
+        }
       }
     }
   } else {
@@ -212,22 +245,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t lane16 = (uint32_t)(quad * 32 + hr * 16);
     const uint32_t lane_base = tmem + (lane16 << 16);
     const int c4 = lane & 3, r8 = lane >> 2;
+    uint32_t g = 0, ui = 0;                                        // K/V tiles / work units processed so far by this CTA (barrier phases)
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
+    int q0, head, bat, split, j_begin, T;
+    decode(u, q0, head, bat, split, j_begin, T);
     float m_refA = -INFINITY, m_refB = -INFINITY;                  // exponent references of rows rA / rB (raw S units)
     float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
     int t = j_begin % tps;
-    for (int j = 0; j < T; ++j, ++t) {
+    for (int j = 0; j < T; ++j, ++t, ++g) {
       if (t == tps) t = 0;
       const int valid = min(BN, lseg - t * BN);
-      mbar_wait(&sm.s_full, (uint32_t)j & 1u);
+      mbar_wait(&sm.s_full, g & 1u);
       tc_fence_after();
-      if (threadIdx.x == 0) DF_TR(0, j);
+      if (threadIdx.x == 0) DF_TR(0, g);
       uint32_t sr[64];
       tmem_ld_16x256b_x16(lane_base + COL_S, sr);
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
-      if (threadIdx.x == 0) DF_TR(1, j);
+      if (threadIdx.x == 0) DF_TR(1, g);
       if (valid < BN) {                              // ragged last tile of a segment only (warp-uniform branch)
         asm volatile("" ::: "memory");
 #pragma unroll
@@ -249,7 +286,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
       mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
       mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-      if (threadIdx.x == 0) DF_TR(2, j);
+      if (threadIdx.x == 0) DF_TR(2, g);
       // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
       float alphaA = 1.f, alphaB = 1.f;
       bool moved = false;
@@ -283,11 +320,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           pr[2 * ii + 1] = pack_h2(b0, b1);
         }
         if (hf == 0) {
-          if (threadIdx.x == 0) DF_TR(3, j);
+          if (threadIdx.x == 0) DF_TR(3, g);
           if (j > 0) {
-            mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
+            mbar_wait(&sm.pv_done, (g - 1) & 1u);  // P buffer free, O quiescent
             tc_fence_after();
-            if (threadIdx.x == 0) DF_TR(4, j);
+            if (threadIdx.x == 0) DF_TR(4, g);
             if (__any_sync(0xffffffffu, moved)) {            // rare: rescale this warp's 16 rows of O
 #pragma unroll
               for (int blk = 0; blk < NBLK; ++blk) {
@@ -317,26 +354,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full);
-      if (threadIdx.x == 0) DF_TR(5, j);
+      if (threadIdx.x == 0) DF_TR(5, g);
     }
     // ---- epilogue: row sums / references -> shared memory (quad reduce), then O / l -> fp16 -> HBM in the 32x32b layout
     //      (thread = row, 16-byte stores): warp w writes columns [32*(w>>2), +32) of the 32 rows of its lane quarter
     lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
     lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
     if (c4 == 0) {
-      sm.red_sum[0][lane16 + r8] = lA; sm.red_sum[0][lane16 + r8 + 8] = lB;
-      sm.red_ref[lane16 + r8] = m_refA; sm.red_ref[lane16 + r8 + 8] = m_refB;
+      sm.red_sum[ui & 1][lane16 + r8] = lA; sm.red_sum[ui & 1][lane16 + r8 + 8] = lB;
+      sm.red_ref[ui & 1][lane16 + r8] = m_refA; sm.red_ref[ui & 1][lane16 + r8 + 8] = m_refB;
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const int half = hr;
     const int row = quad * 32 + lane;
     const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
-    const float l_row = sm.red_sum[0][row];
-    const float m_ref = sm.red_ref[row];
+    const float l_row = sm.red_sum[ui & 1][row];        // [unit parity]: a fast warp may already be filling the next unit's sums
+    const float m_ref = sm.red_ref[ui & 1][row];
     const float inv_l = 1.f / l_row;
-    mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
+    mbar_wait(&sm.pv_done, (g - 1) & 1u);
     tc_fence_after();
-    const int64_t prow = (((int64_t)split * gridDim.z / kv_splits + bat) * heads + head) * lq + q0 + row;   // partial-result row
+    const int64_t prow = (((int64_t)split * (nbz / kv_splits) + bat) * heads + head) * lq + q0 + row;   // partial-result row
     if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
@@ -344,6 +381,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int col0 = blk * HB + half * 32;        // first head column of this chunk
       tmem_ld32(row_base + COL_O + col0, o);
       tmem_wait_ld();
+      if (blk == NBLK - 1) {                        // O is in registers: the next unit's first P V may overwrite the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.o_free);
+      }
       if (q0 + row < lq) {
         if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
           float* dst = part_o + prow * (NBLK * HB) + col0;
@@ -367,21 +409,26 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+    }   // work units
 #else
     const int quad = warp & 3, half = warp >> 2;                   // TMEM lane quarter, S column half
     const int row = quad * 32 + lane;                              // == TMEM lane
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t pair_bar = 1 + quad;                            // named barrier shared by warps `quad` and `quad + 4`
     constexpr int HN = BN / 2;                                     // S columns per thread
+    uint32_t g = 0;                                                // K/V tiles processed so far by this CTA (barrier phases)
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int q0, head, bat, split, j_begin, T;
+    decode(u, q0, head, bat, split, j_begin, T);
     float m_ref = -INFINITY;                                       // max used as exponent reference (raw S units)
     float l = 0.f;                                                 // partial row sum over this thread's columns
     int t = j_begin % tps;                                         // tile inside the current segment
-    for (int j = 0; j < T; ++j, ++t) {
+    for (int j = 0; j < T; ++j, ++t, ++g) {
       if (t == tps) t = 0;
       const int valid = min(BN, lseg - t * BN) - half * HN;        // valid columns inside this thread's half
-      mbar_wait(&sm.s_full, (uint32_t)j & 1u);
+      mbar_wait(&sm.s_full, g & 1u);
       tc_fence_after();
-      if (threadIdx.x == 0) DF_TR(0, j);
+      if (threadIdx.x == 0) DF_TR(0, g);
       uint32_t sr[HN];
       const uint32_t s_addr = lane_base + COL_S + half * HN;
       tmem_ld32(s_addr + 0, sr + 0);
@@ -390,7 +437,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
-      if (threadIdx.x == 0) DF_TR(1, j);
+      if (threadIdx.x == 0) DF_TR(1, g);
       if (valid < HN) {                          // ragged last tile of a segment only
         asm volatile("" ::: "memory");            // keep this a real (warp-uniform) branch: if-converted it costs 2 instr / element on every tile
 #pragma unroll
@@ -410,7 +457,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       sm.red_max[j & 1][half][row] = pm;
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
       const float m_new = max3(pm, sm.red_max[j & 1][half ^ 1][row], m_ref);
-      if (threadIdx.x == 0) DF_TR(2, j);
+      if (threadIdx.x == 0) DF_TR(2, g);
       // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
       float alpha = 1.f;
       bool moved = false;
@@ -443,11 +490,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       float sum0, sum1;
       unpack2(add2(sum2, sum2b), sum0, sum1);
       l += sum0 + sum1;
-      if (threadIdx.x == 0) DF_TR(3, j);
+      if (threadIdx.x == 0) DF_TR(3, g);
       if (j > 0) {
-        mbar_wait(&sm.pv_done, (uint32_t)(j - 1) & 1u);  // P buffer free, O quiescent
+        mbar_wait(&sm.pv_done, (g - 1) & 1u);  // P buffer free, O quiescent
         tc_fence_after();
-        if (threadIdx.x == 0) DF_TR(4, j);
+        if (threadIdx.x == 0) DF_TR(4, g);
         if (__any_sync(0xffffffffu, moved)) {            // this warp owns O columns [64*blk + 32*half, +32) of every block
 #pragma unroll
           for (int blk = 0; blk < NBLK; ++blk) {
@@ -465,16 +512,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.p_full);
-      if (threadIdx.x == 0) DF_TR(5, j);
+      if (threadIdx.x == 0) DF_TR(5, g);
     }
     // ---- epilogue: O / l -> fp16 -> HBM (each half-row warp writes its 32 columns)
     sm.red_sum[half][row] = l;
     asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
     const float l_row = sm.red_sum[0][row] + sm.red_sum[1][row];
     const float inv_l = 1.f / l_row;
-    mbar_wait(&sm.pv_done, (uint32_t)(T - 1) & 1u);
+    mbar_wait(&sm.pv_done, (g - 1) & 1u);
     tc_fence_after();
-    const int64_t prow = (((int64_t)split * gridDim.z / kv_splits + bat) * heads + head) * lq + q0 + row;   // partial-result row
+    const int64_t prow = (((int64_t)split * (nbz / kv_splits) + bat) * heads + head) * lq + q0 + row;   // partial-result row
     if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
 #pragma unroll
     for (int blk = 0; blk < NBLK; ++blk) {
@@ -482,6 +529,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       const int col0 = blk * HB + half * 32;        // first head column of this chunk
       tmem_ld32(lane_base + COL_O + col0, o);
       tmem_wait_ld();
+      if (blk == NBLK - 1) {                        // O is in registers: the next unit's first P V may overwrite the accumulator
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.o_free);
+      }
       if (q0 + row < lq) {
         if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
           float* dst = part_o + prow * (NBLK * HB) + col0;
@@ -505,6 +557,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+    }   // work units
 #endif
   }
   tc_fence_before();
@@ -656,11 +709,16 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   const int nblk = (d + HB - 1) / HB;
   int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
   if (splits > 1 && (workspace == nullptr || workspace_bytes < df_attn_workspace_bytes(b, lq, lseg, nseg, heads, d))) splits = 1;
-  DF_REQUIRE((long long)b * splits <= 65535, "df_attn_fwd: grid too large");
   const int64_t rows = (int64_t)b * heads * lq;
   float2* part_ml = (float2*)workspace;                                   // [splits][rows]
   float* part_o = splits > 1 ? (float*)((char*)workspace + (((size_t)splits * rows * sizeof(float2) + 255) / 256) * 256) : nullptr;
-  dim3 grid((lq + BM - 1) / BM, heads, b * splits);
+  // persistent CTAs: one per resident slot (2 per SM for d <= 64, else 1), each walking the work units round-robin
+  static int sm_count = 0;
+  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
+  const long long n_units = (long long)((lq + BM - 1) / BM) * heads * b * splits;
+  DF_REQUIRE(n_units < (1ll << 31), "df_attn_fwd: too many work units");
+  const long long slots = (long long)sm_count * (nblk == 1 ? Cfg<1>::CTAS : 1);
+  dim3 grid((unsigned)(n_units < slots ? n_units : slots), 1, 1);
 #define DF_LAUNCH_FMHA(NB)                                                                                                  \
   {                                                                                                                          \
     static bool attr_set = false;                                                                                            \
@@ -671,7 +729,7 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
     }                                                                                                                        \
     fmha_fwd_kernel<NB><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(                                               \
         tq, tkv, (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg, own_seg, idx,      \
-        wait_flags, sc, splits, part_o, part_ml);                                                                            \
+        wait_flags, sc, splits, b * splits, part_o, part_ml);                                                                \
   }
   if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA

@@ -60,10 +60,13 @@ struct GnExchange {   // everything the last CTA needs to finish the statistics 
 
 __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine);
 
-__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
-                                                       float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
-                                                       int ppc, GnExchange ex) {
-  extern __shared__ float2 ch[];  // [lanes][C] per-channel (sum, sum of squares); reused as float2 mine[bG] by the last CTA
+// Statistics pass of one CTA; returns true in the LAST CTA of the grid after it has run the exchange and written coef[].
+// STREAM = true: loads bypass L1 (two-kernel path: the data is touched once); false: default caching, so that the apply pass
+// of the fused kernel finds this CTA's pixels in L1 / L2.
+template <bool STREAM>
+__device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                              float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
+                                              int ppc, const GnExchange& ex, float2* ch) {
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int tid = threadIdx.x;
   const int v = tid % V, pl = tid / V;
@@ -75,12 +78,13 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = ad[j] = 0.f;
     if (addend) unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);   // per-(sample, channel) bias, e.g. the time embedding
     int p = p0 + pl;
-    for (; p + 3 * lanes < p1; p += 4 * lanes) {
-      int4 r[4];
+    constexpr int U = 8;                          // loads in flight per thread (one DRAM latency round per 8 pixels)
+    for (; p + (U - 1) * lanes < p1; p += U * lanes) {
+      int4 r[U];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) r[u] = ld_nc_v4(base + (size_t)(p + u * lanes) * C);
+      for (int u = 0; u < U; ++u) r[u] = STREAM ? ld_nc_v4(base + (size_t)(p + u * lanes) * C) : ld_v4(base + (size_t)(p + u * lanes) * C);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < U; ++u) {
         float f[8];
         unpack8(r[u], f);
 #pragma unroll
@@ -89,7 +93,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
     }
     for (; p < p1; p += lanes) {
       float f[8];
-      unpack8(ld_nc_v4(base + (size_t)p * C), f);
+      unpack8(STREAM ? ld_nc_v4(base + (size_t)p * C) : ld_v4(base + (size_t)p * C), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) { float t = f[j] + ad[j]; s[j] += t; ss[j] = fmaf(t, t, ss[j]); }
     }
@@ -128,9 +132,17 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
     if (is_last) *ex.ticket = 0;
   }
   __syncthreads();
-  if (!is_last) return;
+  if (!is_last) return false;
   __threadfence();
   gn_exchange(ex, partial, G, nchunk, ch);
+  return true;
+}
+
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                                       float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
+                                                       int ppc, GnExchange ex) {
+  extern __shared__ float2 ch[];  // [lanes][C] per-channel (sum, sum of squares); reused as float2 mine[bG] by the last CTA
+  gn_stats_body<true>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch);
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
@@ -210,11 +222,12 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
   if (mode >= 2) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
 }
 
-__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
-                                                       __half* __restrict__ y, const __half* __restrict__ gamma,
-                                                       const __half* __restrict__ beta,
-                                                       const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
-                                                       int ppc, int silu) {
+template <bool STREAM>
+__device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                              __half* __restrict__ y, const __half* __restrict__ gamma,
+                                              const __half* __restrict__ beta,
+                                              const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
+                                              int ppc, int silu) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
   const int v = tid % V, pl = tid / V;
@@ -224,7 +237,8 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     int ch = v * 8 + j;
-    float2 mr = coef[b * G + ch / cpg];
+    float2 mr;                       // plain (coherent) load: in the fused kernel coef[] was written during this launch
+    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(mr.x), "=f"(mr.y) : "l"(coef + b * G + ch / cpg) : "memory");
     float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
     sc[j] = mr.y * ga;
     sh[j] = be - mr.x * sc[j];
@@ -256,11 +270,51 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
   for (; p + 3 * lanes < p1; p += 4 * lanes) {
     int4 r[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = ld_nc_v4(x + base + (size_t)(p + u * lanes) * C);
+    for (int u = 0; u < 4; ++u) r[u] = STREAM ? ld_nc_v4(x + base + (size_t)(p + u * lanes) * C) : ld_v4(x + base + (size_t)(p + u * lanes) * C);
 #pragma unroll
     for (int u = 0; u < 4; ++u) st_v4(y + base + (size_t)(p + u * lanes) * C, xform(r[u]));
   }
-  for (; p < p1; p += lanes) st_v4(y + base + (size_t)p * C, xform(ld_nc_v4(x + base + (size_t)p * C)));
+  for (; p < p1; p += lanes) st_v4(y + base + (size_t)p * C, xform(STREAM ? ld_nc_v4(x + base + (size_t)p * C) : ld_v4(x + base + (size_t)p * C)));
+}
+
+__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                                       __half* __restrict__ y, const __half* __restrict__ gamma,
+                                                       const __half* __restrict__ beta,
+                                                       const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
+                                                       int ppc, int silu) {
+  gn_apply_body<true>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu);
+}
+
+// ONE launch: statistics -> grid-wide hand-over -> normalise.  Every CTA of the grid is resident at once (the host caps the
+// grid at the occupancy of this kernel), so the CTAs that finished their partial moments may spin on the generation word
+// that the last CTA bumps after it has reduced / exchanged the statistics and written coef[]; then each CTA normalises the
+// pixels it has just read (L1 / L2 hits: one HBM read and one write per element instead of two reads and one write, and one
+// launch instead of two -- the level-2 GroupNorms of SDXL are launch-bound).
+__global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+                                                          __half* __restrict__ y, const __half* __restrict__ gamma,
+                                                          const __half* __restrict__ beta, float2* __restrict__ partial,
+                                                          const float2* __restrict__ coef, int hw, int C, int G, int V,
+                                                          int lanes, int ppc, int silu, GnExchange ex, unsigned int* gen) {
+  extern __shared__ float2 ch[];
+  __shared__ unsigned int my_gen;
+  if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
+  __syncthreads();
+  const bool last = gn_stats_body<false>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch);
+  if (last) {
+    __threadfence();                                     // coef[] (written by this CTA's threads) before the generation bump
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(my_gen + 1u) : "memory");
+  } else {
+    if (threadIdx.x == 0) {
+      unsigned int v;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gen) : "memory");
+        if (v == my_gen) __nanosleep(40);
+      } while (v == my_gen);
+    }
+    __syncthreads();
+  }
+  gn_apply_body<false>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu);
 }
 
 }  // namespace
@@ -297,6 +351,24 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   ex.tensor_off = tensor_off; ex.slot_bytes = slot_bytes; ex.group_mask = group_mask;
   size_t smem = (size_t)p.lanes * C * sizeof(float2);           // <= 32 KiB (lanes * C <= 4096)
   if (smem < (size_t)b * groups * sizeof(float2)) smem = (size_t)b * groups * sizeof(float2);
+  // one launch when the whole grid is resident at once (always, for the plans of gn_plan on a B200: <= 2 CTAs per SM)
+  static int fused_capacity = -1;
+  if (fused_capacity < 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, 512, 32 * 1024) != cudaSuccess) per_sm = 0;
+    fused_capacity = per_sm * sms;
+    cudaGetLastError();
+  }
+  if (p.nchunk * b <= fused_capacity && smem <= 32 * 1024) {
+    unsigned int* gen = ticket + 1;
+    gn_fused_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, (__half*)y,
+                                                              (const __half*)gamma, (const __half*)beta, partial, coef, hw, C,
+                                                              groups, p.V, p.lanes, p.ppc, fuse_silu, ex, gen);
+    DF_CHECK_LAUNCH();
+    return 0;
+  }
   gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, partial, hw, C, groups,
                                                              p.V, p.lanes, p.ppc, ex);
   DF_CHECK_LAUNCH();

@@ -33,28 +33,27 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity) {
-  const uint64_t t0 = globaltimer_ns();
-  for (;;) {
-#pragma unroll 1
-    for (int i = 0; i < 4096; ++i)
-      if (mbar_try(bar, parity)) return;
-    if (globaltimer_ns() - t0 > 10000000000ull) {      // a broken pipeline becomes a CUDA error instead of a hung GPU
-      printf("distrifuser_b200 fmha: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-      __trap();
+// Waits for the phase with the given parity.  try_wait suspends the thread in hardware for up to DF_TRYWAIT_HINT_NS, so the loop
+// costs two instructions per poll.  Fully inline on purpose: an out-of-line slow path (ABI call + printf) inside the softmax
+// loop made ptxas spill around the call site.  A broken pipeline still becomes a CUDA error instead of a hung GPU: after ~10 s
+// of failed polls the thread traps (define DF_MBAR_DEBUG for a printf naming the barrier).
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try(bar, parity)) {
+    if ((++polls & 0x3FFu) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 10000000000ull) {
+#ifdef DF_MBAR_DEBUG
+        printf("distrifuser_b200: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x, smem_u32(bar), parity);
+#endif
+        __trap();
+      }
     }
   }
-}
-#ifndef DF_SPIN_FAST_POLLS
-#define DF_SPIN_FAST_POLLS 1
-#endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  // try_wait suspends the thread for a hardware time slice, so this loop is two instructions per poll
-#pragma unroll 1
-  for (int i = 0; i < DF_SPIN_FAST_POLLS; ++i)
-    if (mbar_try(bar, parity)) return;
-  mbar_wait_slow(bar, parity);
 }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {

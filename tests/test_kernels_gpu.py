@@ -43,6 +43,10 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (1, 256, 8192, 4, 64),         # tiny grid, long K/V: split-KV (8 CTAs per q-tile) + combine kernel
     (1, 130, 4100, 3, 64),         # split-KV with ragged q and k/v tiles
     (1, 100, 3000, 2, 40),         # split-KV, zero-padded head dim
+    (2, 4096, 77, 10, 64),         # persistent CTAs: 640 one-tile work units on 296 resident CTAs (cross-attention at 1024^2 level 1)
+    (2, 2048, 300, 20, 64),        # persistent CTAs: 640 units x 3 tiles, ragged last tile
+    (2, 1100, 520, 8, 80),         # persistent CTAs, two head blocks, one CTA per SM: 144 units (< 148) and ragged q
+    (2, 2304, 260, 8, 160),        # persistent CTAs, three head blocks: 288 units on 148 CTAs
 ])
 def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)

@@ -28,16 +28,17 @@ using namespace df::tc;
 namespace {
 
 constexpr int BM = 128;            // rows of A per CTA (256 per pair)
-constexpr int BN = 256;            // output-tile columns (W rows); each CTA stages BN/2 of them
+// BN = output-tile columns (W rows) of a pair; each CTA stages BN/2 of them.  256 for large N and the GEGLU epilogue; 160 where 256
+// would leave most pairs idle (N = 1280 with M = 2048: 40 tiles on 74 pairs -> 64 tiles).  UMMA: M = 256 needs N % 16 == 0.
 constexpr int BK = 64;             // one 128-byte swizzled row of fp16
 constexpr int STAGES = 6;
 constexpr int NTHREADS = 192;
-constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2;
-constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+constexpr uint32_t A_BYTES = BM * BK * 2;
 
-struct __align__(1024) Smem {
+template <int BN>
+struct __align__(1024) SmemT {
   __half a[STAGES][BM * BK];
-  __half b[STAGES][(BN / 2) * BK];
+  __half b[STAGES][(BN / 2) * BK];         // (BN / 2) * 128 B per stage: a multiple of 1 KiB for BN in {160, 256}
   uint64_t full[STAGES], empty[STAGES];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
@@ -84,9 +85,13 @@ __device__ __forceinline__ void unpack8h(const int4& v, float* f) {
   }
 }
 
-template <int EPI>
+template <int EPI, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, LinearArgs p) {
+  static_assert(BN % 32 == 0 && BN <= 256 && ((BN / 2) * BK * 2) % 1024 == 0, "tile shape");
+  constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+  using Smem = SmemT<BN>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
@@ -315,23 +320,30 @@ int make_map2d(CUtensorMap* m, const void* base, int64_t rows, int K, int64_t pi
   return 0;
 }
 
-template <int EPI>
+template <int EPI, int BN>
 int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const LinearArgs& args, int ctas, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    DF_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+    DF_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<BN>)));
     attr_set = true;
   }
-  linear_kernel<EPI><<<ctas, NTHREADS, sizeof(Smem), st>>>(ta, tw, args);      // cluster size 2 comes from __cluster_dims__
+  linear_kernel<EPI, BN><<<ctas, NTHREADS, sizeof(SmemT<BN>), st>>>(ta, tw, args);      // cluster size 2 comes from __cluster_dims__
   DF_CHECK_LAUNCH();
   return 0;
+}
+
+// share of the pair-rounds x tile area that does useful work: wave quantisation x column padding
+double tile_efficiency(int64_t M, int N, int bn, int pairs_avail) {
+  const long long tm = (M + 2 * BM - 1) / (2 * BM), tn = (N + bn - 1) / bn, tiles = tm * tn;
+  const long long rounds = (tiles + pairs_avail - 1) / pairs_avail;
+  return (double)tiles / (double)(rounds * pairs_avail) * ((double)N / (double)(tn * bn));
 }
 
 }  // namespace
 
 extern "C" int df_linear_supported(int64_t M, int N, int K, int epilogue) {
   if (M < 1 || N < 8 || N % 8 != 0 || K < BK || K % BK != 0) return 0;
-  if (epilogue == EPI_GEGLU && N % BN != 0) return 0;     // hidden/gate blocks of 128 must tile the interleaved weight exactly
+  if (epilogue == EPI_GEGLU && N % 256 != 0) return 0;    // hidden/gate blocks of 128 must tile the interleaved weight exactly
   return 1;
 }
 
@@ -350,8 +362,13 @@ extern "C" int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const
   memset(&args, 0, sizeof(args));
   args.bias = (const __half*)bias; args.residual = (const __half*)residual; args.out = (__half*)out;
   args.M = M; args.N = N; args.K = K; args.ldr = ldr; args.ldo = ldo;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int cap = (max_ctas > 0 ? max_ctas : sms) / 2 > 0 ? (max_ctas > 0 ? max_ctas : sms) / 2 : 1;
+  int bn = 256;
+  if (epilogue == EPI_PLAIN && tile_efficiency(M, N, 160, cap) > tile_efficiency(M, N, 256, cap) + 0.02) bn = 160;
   args.tiles_m = (int)((M + 2 * BM - 1) / (2 * BM));
-  args.tiles_n = (N + BN - 1) / BN;
+  args.tiles_n = (N + bn - 1) / bn;
   args.publish = publish && peer_mask != 0;
   args.comm = comm;
   if (args.publish) {
@@ -360,16 +377,14 @@ extern "C" int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const
     args.tensor_off = tensor_off; args.slot_bytes = slot_bytes;
     DF_REQUIRE((uint64_t)M * args.pub_cols * 2 <= slot_bytes, "df_linear_fwd: published columns larger than the slot");
   }
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   int pairs = args.tiles_m * args.tiles_n;
-  int cap = (max_ctas > 0 ? max_ctas : sms) / 2;
   if (pairs > cap) pairs = cap;
   if (pairs < 1) pairs = 1;
   CUtensorMap ta, tw;
   if (int rc = make_map2d(&ta, a, M, K, lda, BM)) return rc;
-  if (int rc = make_map2d(&tw, w, N, K, ldw, BN / 2)) return rc;
+  if (int rc = make_map2d(&tw, w, N, K, ldw, bn / 2)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (epilogue == EPI_GEGLU) return launch_linear<EPI_GEGLU>(ta, tw, args, 2 * pairs, st);
-  return launch_linear<EPI_PLAIN>(ta, tw, args, 2 * pairs, st);
+  if (epilogue == EPI_GEGLU) return launch_linear<EPI_GEGLU, 256>(ta, tw, args, 2 * pairs, st);
+  if (bn == 160) return launch_linear<EPI_PLAIN, 160>(ta, tw, args, 2 * pairs, st);
+  return launch_linear<EPI_PLAIN, 256>(ta, tw, args, 2 * pairs, st);
 }

@@ -14,7 +14,7 @@ from distrifuser_b200 import _lib, ops  # noqa: E402
 L = _lib.lib()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-which = set((sys.argv[1] if len(sys.argv) > 1 else "attn,gn,geglu,ln,publish").split(","))
+which = set((sys.argv[1] if len(sys.argv) > 1 else "attn,gn,geglu,ln,publish,linear").split(","))
 
 
 def profiled(fn):
@@ -68,4 +68,19 @@ if "publish" in which:
     arena.set_clock(pub=1, rd=1)
     profiled(lambda: _lib.check(L.df_slot_publish(arena.comm, src.data_ptr(), 1, nbytes, nbytes, arena.tensor_off[0], arena.slot_bytes[0],
                                                   0, 0b10, 64, st), "publish"))
+if "linear" in which:
+    # level-2 feed-forward of SDXL at 1024^2 (CFG pair): fused GEGLU projection, and the plain FF2 / to_out shapes
+    M, K, D = 2048, 1280, 5120
+    x = torch.randn(M, K, device="cuda").half()
+    w = (torch.randn(2 * D, K, device="cuda") / K ** 0.5).half()
+    bias = torch.randn(2 * D, device="cuda").half()
+    wi, bi = ops.geglu_interleave(w, bias)
+    profiled(lambda: ops.linear_geglu(x, wi, bi))
+    h = torch.randn(M, D, device="cuda").half()
+    w2 = (torch.randn(K, D, device="cuda") / D ** 0.5).half()
+    b2 = torch.randn(K, device="cuda").half()
+    r = torch.randn(M, K, device="cuda").half()
+    profiled(lambda: ops.linear(h, w2, b2, r))
+    wq = (torch.randn(3 * K, K, device="cuda") / K ** 0.5).half()
+    profiled(lambda: ops.linear(x, wq))
 print("done")

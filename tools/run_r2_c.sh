@@ -1,0 +1,15 @@
+# round 2, GPU call C: attention v4 (software-pipelined) tests + variant sweep with graph timing, GroupNorm fused tests, GEMM graph timing + ncu
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_linear_gpu.py -q -x > gpurun_out/r2c_kernel_tests.log 2>&1; tail -6 gpurun_out/r2c_kernel_tests.log
+timeout 300 python tools/bench_linear.py 1024 > gpurun_out/r2c_linear_vs_cublas.txt 2>&1; cat gpurun_out/r2c_linear_vs_cublas.txt
+SH="1024_l1,1024_l2,3840n4_l2,1024n4_l2,1024n4_l1,cross_l2"
+rm -f gpurun_out/r2c_attn_sweep.txt
+for V in "-DDF_FMHA_PIPE=1 -DDF_PIPE_PREFETCH_AT=2" "-DDF_FMHA_PIPE=1 -DDF_PIPE_PREFETCH_AT=0" "-DDF_FMHA_PIPE=1 -DDF_PIPE_PREFETCH_AT=2 -DDF_EMU_QUARTERS=0" "-DDF_FMHA_PIPE=1 -DDF_PIPE_PREFETCH_AT=2 -DDF_EMU_QUARTERS=2" "-DDF_FMHA_PIPE=0"; do
+  echo "== variant: $V" >> gpurun_out/r2c_attn_sweep.txt
+  DF_NVCC_FLAGS="$V" python -c "from distrifuser_b200 import build; build.build(force=True)" >> gpurun_out/r2c_build.log 2>&1
+  timeout 300 python tools/bench_attn.py --shapes $SH >> gpurun_out/r2c_attn_sweep.txt 2>&1
+done
+python -c "from distrifuser_b200 import build; build.build(force=True)" >> gpurun_out/r2c_build.log 2>&1
+cat gpurun_out/r2c_attn_sweep.txt
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -f -o gpurun_out/r2c_kernels python tools/ncu_kernels.py attn,attn3840,gn,linear > gpurun_out/r2c_ncu.log 2>&1; tail -3 gpurun_out/r2c_ncu.log
+python tools/bench_vs_torch.py > gpurun_out/r2c_vs_torch.txt 2>&1; cat gpurun_out/r2c_vs_torch.txt

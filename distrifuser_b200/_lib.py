@@ -17,7 +17,7 @@ TENSORMAP_BYTES = 128
 EXPORTS = (
     "df_last_error", "df_version", "df_device_sm_count", "df_symm_alloc", "df_symm_open", "df_symm_close",
     "df_symm_free", "df_step_begin", "df_slot_publish", "df_slot_wait", "df_groupnorm_scratch_bytes",
-    "df_groupnorm_fwd", "df_halo_push", "df_halo_assemble", "df_attn_make_kvmaps", "df_attn_workspace_bytes", "df_attn_fwd",
+    "df_groupnorm_fwd", "df_groupnorm_halo_fwd", "df_halo_push", "df_halo_assemble", "df_attn_make_kvmaps", "df_attn_workspace_bytes", "df_attn_fwd",
     "df_output_gather", "df_geglu", "df_add_layernorm", "df_linear_supported", "df_linear_fwd",
 )
 
@@ -54,6 +54,8 @@ def lib():
         L.df_groupnorm_scratch_bytes.restype = C.c_size_t
         L.df_groupnorm_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
                                        u64, u64, u32, vp, vp]
+        L.df_groupnorm_halo_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
+                                            u64, u64, u32, vp, i32, u64, u64, i32, i32, i32, i32, vp]
         L.df_halo_push.argtypes = [DfComm, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, vp]
         L.df_halo_assemble.argtypes = [DfComm, vp, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, i32, vp]
         L.df_attn_make_kvmaps.argtypes = [DfComm, u64, u64, i32, i32, i32, i32, vp, vp]
@@ -74,7 +76,7 @@ def lib():
 
 
 # kernels launched per C-ABI call (bench.py reports the count of OUR launches inside the timed region)
-KERNELS_PER_CALL = {"df_groupnorm_fwd": 1, "df_attn_fwd": 1, "df_halo_push": 1, "df_halo_assemble": 1,
+KERNELS_PER_CALL = {"df_groupnorm_fwd": 1, "df_groupnorm_halo_fwd": 1, "df_attn_fwd": 1, "df_halo_push": 1, "df_halo_assemble": 1,
                     "df_slot_publish": 1, "df_slot_wait": 1, "df_step_begin": 1, "df_output_gather": 2, "df_geglu": 1, "df_add_layernorm": 1,
                     "df_linear_fwd": 1}
 LAUNCHES = {"total": 0}

@@ -191,16 +191,23 @@ class ResnetBlock2D(nn.Module):
         self.fused_norm_act = False      # DistriUNetPP turns this on: SiLU runs inside the GroupNorm kernel
 
     def forward(self, x, temb):
-        h = self.norm1(x)
-        if not self.fused_norm_act:
-            h = self.nonlinearity(h)
-        h = self.conv1(h)
-        t = self.time_emb_proj(self.nonlinearity(temb))
-        if self.fused_norm_act:
-            h = self.norm2(h, addend=t)          # GroupNorm(h + t[:, :, None, None]) + SiLU in one kernel pair
+        fused_halo = self.fused_norm_act and hasattr(self.conv1, "halo_plan")    # DistriGroupNorm -> DistriConv2dPP pairs
+        if fused_halo and self.conv1.halo_plan(x) is not None:
+            h = self.conv1.forward_padded(self.norm1(x, pad_for=self.conv1))     # norm + SiLU + halo rows in ONE kernel
         else:
-            h = self.nonlinearity(self.norm2(h + t[:, :, None, None]))
-        h = self.conv2(h)
+            h = self.norm1(x)
+            if not self.fused_norm_act:
+                h = self.nonlinearity(h)
+            h = self.conv1(h)
+        t = self.time_emb_proj(self.nonlinearity(temb))
+        if fused_halo and self.conv2.halo_plan(h) is not None:
+            h = self.conv2.forward_padded(self.norm2(h, addend=t, pad_for=self.conv2))
+        else:
+            if self.fused_norm_act:
+                h = self.norm2(h, addend=t)      # GroupNorm(h + t[:, :, None, None]) + SiLU in one kernel
+            else:
+                h = self.nonlinearity(self.norm2(h + t[:, :, None, None]))
+            h = self.conv2(h)
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -367,8 +374,11 @@ class UNet2DConditionModel(nn.Module):
         x = self.mid_block(x, emb, encoder_hidden_states)
         for blk in self.up_blocks:
             x = blk(x, skips, emb, encoder_hidden_states)
-        x = self.conv_norm_out(x)
-        if not self.fused_norm_act:
-            x = self.conv_act(x)
-        x = self.conv_out(x)
+        if self.fused_norm_act and hasattr(self.conv_out, "halo_plan") and self.conv_out.halo_plan(x) is not None:
+            x = self.conv_out.forward_padded(self.conv_norm_out(x, pad_for=self.conv_out))
+        else:
+            x = self.conv_norm_out(x)
+            if not self.fused_norm_act:
+                x = self.conv_act(x)
+            x = self.conv_out(x)
         return UNet2DConditionOutput(x) if return_dict else (x,)

@@ -137,6 +137,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  pdl_wait();                                          // everything above overlapped the tail of the previous kernel
 
   if (warp == WARP_TMA) {
     // =============================================================== TMA producer
@@ -804,9 +805,9 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
       DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
       attr_set = true;                                                                                                       \
     }                                                                                                                        \
-    fmha_fwd_kernel<NB><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(                                               \
-        tq, tkv, (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg, own_seg, idx,      \
-        wait_flags, sc, splits, b * splits, part_o, part_ml);                                                                \
+    DF_CHECK_CUDA(launch_pdl(fmha_fwd_kernel<NB>, grid, dim3(NTHREADS), smem_bytes, (cudaStream_t)stream, tq, tkv,           \
+                             (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg,        \
+                             own_seg, idx, wait_flags, sc, splits, b * splits, part_o, part_ml));                            \
   }
   if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA

@@ -2,6 +2,7 @@
 // final epsilon gather.  Replaces PatchParallelismCommManager (distrifuser/utils.py:112-199) and the
 // blocking collectives of the pp modules (attn.py:133, conv2d.py:93, distri_sdxl_unet_pp.py:166,191).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 }  // namespace df
+
+bool df::pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DF_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 using namespace df;
 

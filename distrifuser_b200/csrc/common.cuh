@@ -86,6 +86,30 @@ __device__ __forceinline__ void st_v4(void* p, const int4& v) {
   asm volatile("st.global.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A denoise step is a chain of ~1 400 short kernels; with the launch attribute below a kernel of this library may be scheduled
+// while its predecessor in the stream is still draining, run its prologue (TMEM / barrier set-up, tensor-map prefetch, index
+// arithmetic) and then block in pdl_wait() until the predecessor has completed and flushed its writes.  No global memory is
+// read or written before pdl_wait().  DF_PDL=0 in the environment disables the attribute (the device-side wait is then a no-op).
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ char* slot_ptr(const df_comm_t& c, int rank, uint32_t epoch, uint64_t tensor_off,
                                           uint64_t slot_bytes, int src) {
   return (char*)c.base[rank] + (uint64_t)(epoch % DF_NBANKS) * c.bank_stride + tensor_off + (uint64_t)src * slot_bytes;

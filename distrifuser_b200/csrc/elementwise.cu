@@ -25,6 +25,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __global__ void __launch_bounds__(256) geglu_kernel(const __half* __restrict__ in, __half* __restrict__ out, int64_t rows,
                                                     int vec_per_row, int64_t in_pitch, int64_t out_pitch, int cols) {
   const int64_t total = rows * vec_per_row;
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / vec_per_row;
     const int q = (int)(i - r * vec_per_row);
@@ -52,8 +53,8 @@ extern "C" int df_geglu(const void* in, void* out, int64_t rows, int cols, int64
   const int64_t total = rows * (cols / 8);
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  geglu_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, rows, cols / 8, in_pitch, out_pitch, cols);
-  DF_CHECK_LAUNCH();
+  DF_CHECK_CUDA(launch_pdl(geglu_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, (const __half*)in, (__half*)out, rows,
+                           cols / 8, in_pitch, out_pitch, cols));
   return 0;
 }
 
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const __half* __rest
                                                             int64_t rows, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = C >> 3;
   const __half* xr = x + row * C;
@@ -150,8 +152,8 @@ extern "C" int df_add_layernorm(const void* x, const void* r, void* s_out, void*
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   cudaStream_t st = (cudaStream_t)stream;
   const int nvec = C / 8;
-#define DF_LN(MV) add_layernorm_kernel<MV><<<grid, warps * 32, 0, st>>>((const __half*)x, (const __half*)r, (__half*)s_out, \
-      (__half*)y, (const __half*)gamma, (const __half*)beta, rows, C, eps)
+#define DF_LN(MV) DF_CHECK_CUDA(launch_pdl(add_layernorm_kernel<MV>, dim3(grid), dim3(warps * 32), 0, st, (const __half*)x, (const __half*)r, \
+      (__half*)s_out, (__half*)y, (const __half*)gamma, (const __half*)beta, rows, C, eps))
   if (nvec <= 32 * 2) DF_LN(2); else if (nvec <= 32 * 3) DF_LN(3); else if (nvec <= 32 * 5) DF_LN(5); else DF_LN(8);
 #undef DF_LN
   DF_CHECK_LAUNCH();

@@ -6,6 +6,8 @@
 //                          release/acquire flags over NVLink and applies the mode formula (gn_exchange)
 //   (2) gn_apply_kernel    one read (L2-resident for <= ~60 MB activations) + one write, optional fused SiLU
 // Both accept a per-(sample, channel) addend so that ResnetBlock2D's `conv1(x) + time_emb` never materialises.
+#include <string.h>
+
 #include "common.cuh"
 
 using namespace df;
@@ -56,6 +58,22 @@ struct GnExchange {   // everything the last CTA needs to finish the statistics 
   int mode, neg_fb, idx;
   uint64_t tensor_off, slot_bytes;
   uint32_t group_mask;
+};
+
+// Fused conv-halo handling of the normalise pass (GroupNorm -> SiLU -> 3x3 conv, the ResnetBlock2D pattern): the output goes
+// into the interior rows of a [b, h+2, w, C] buffer, this rank's first / last output rows are ALSO stored into the patch
+// neighbours' arena slots of the conv (replaces df_halo_push), and the two margin rows are filled from the neighbours' slots
+// of the read epoch (replaces df_halo_assemble and its full-activation copy; distrifuser/modules/pp/conv2d.py:72-93).
+struct GnHalo {
+  int enabled;
+  int h, w;                 // local rows, width
+  int up, down;             // patch neighbours (communicator indices) or -1 at the image border
+  int push;                 // ship this call's boundary rows (synchronous step: for this step; asynchronous: for the next one)
+  int wait_flags;
+  int idx;                  // comm tensor index of the CONV
+  uint64_t off, slot_bytes;
+  unsigned int* ticket2;    // CTA ticket of the normalise pass (self-resetting)
+  df_comm_t c;
 };
 
 __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine);
@@ -227,62 +245,120 @@ __device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, cons
                                               __half* __restrict__ y, const __half* __restrict__ gamma,
                                               const __half* __restrict__ beta,
                                               const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
-                                              int ppc, int silu) {
+                                              int ppc, int silu, const GnHalo& halo) {
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int tid = threadIdx.x;
   const int v = tid % V, pl = tid / V;
-  if (pl >= lanes) return;
-  const int cpg = C / G;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int ch = v * 8 + j;
-    float2 mr;                       // plain (coherent) load: in the fused kernel coef[] was written during this launch
-    asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(mr.x), "=f"(mr.y) : "l"(coef + b * G + ch / cpg) : "memory");
-    float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
-    sc[j] = mr.y * ga;
-    sh[j] = be - mr.x * sc[j];
-  }
-  if (addend) {                     // y = ((x + a) - mean) * rstd * gamma + beta  ==  x * sc + (sh + a * sc)
-    float ad[8];
-    unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sh[j] = fmaf(ad[j], sc[j], sh[j]);
-  }
-  const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
-  const size_t base = ((size_t)b * hw) * C + (size_t)v * 8;
-  auto xform = [&](const int4& in) {
-    float f[8];
-    unpack8(in, f);
-    int4 o;
-    __half2* oh = reinterpret_cast<__half2*>(&o);
+  const size_t row_el = halo.enabled ? (size_t)halo.w * C : 0;          // elements of one image row
+  uint32_t pub = 0;
+  if (halo.enabled && halo.push) pub = halo.c.clock[0];
+  if (pl < lanes) {
+    const int cpg = C / G;
+    float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float t = fmaf(f[j], sc[j], sh[j]);
-      if (silu) t = __fdividef(t, 1.f + __expf(-t));
-      f[j] = t;
+      int ch = v * 8 + j;
+      float2 mr;                       // plain (coherent) load: in the fused kernel coef[] was written during this launch
+      asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(mr.x), "=f"(mr.y) : "l"(coef + b * G + ch / cpg) : "memory");
+      float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
+      sc[j] = mr.y * ga;
+      sh[j] = be - mr.x * sc[j];
     }
+    if (addend) {                     // y = ((x + a) - mean) * rstd * gamma + beta  ==  x * sc + (sh + a * sc)
+      float ad[8];
+      unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-    return o;
-  };
-  int p = p0 + pl;
-  for (; p + 3 * lanes < p1; p += 4 * lanes) {
-    int4 r[4];
+      for (int j = 0; j < 8; ++j) sh[j] = fmaf(ad[j], sc[j], sh[j]);
+    }
+    const int p0 = chunk * ppc, p1 = min(hw, p0 + ppc);
+    const size_t base = ((size_t)b * hw) * C + (size_t)v * 8;
+    // padded output: sample b starts at row b*(h+2), the interior at row 1
+    const size_t ybase = halo.enabled ? ((size_t)b * (hw + 2 * halo.w) + halo.w) * C + (size_t)v * 8 : base;
+    // neighbours' slots [2][batch][w*C]: part 0 = the sender's first row, part 1 = its last row (conv2d.py:61-65,90)
+    __half* dst_up = nullptr;
+    __half* dst_dn = nullptr;
+    if (halo.enabled && halo.push) {
+      const size_t nb = gridDim.y;
+      if (halo.up >= 0) dst_up = (__half*)slot_ptr(halo.c, halo.up, pub, halo.off, halo.slot_bytes, halo.c.rank) + ((size_t)b) * row_el + (size_t)v * 8;
+      if (halo.down >= 0) dst_dn = (__half*)slot_ptr(halo.c, halo.down, pub, halo.off, halo.slot_bytes, halo.c.rank) + (nb + b) * row_el + (size_t)v * 8;
+    }
+    const int last_row0 = hw - halo.w;                                  // first pixel of the last row (halo.enabled only)
+    auto xform = [&](const int4& in) {
+      float f[8];
+      unpack8(in, f);
+      int4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) r[u] = STREAM ? ld_nc_v4(x + base + (size_t)(p + u * lanes) * C) : ld_v4(x + base + (size_t)(p + u * lanes) * C);
+      for (int j = 0; j < 8; ++j) {
+        float t = fmaf(f[j], sc[j], sh[j]);
+        if (silu) t = __fdividef(t, 1.f + __expf(-t));
+        f[j] = t;
+      }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) st_v4(y + base + (size_t)(p + u * lanes) * C, xform(r[u]));
+      for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+      return o;
+    };
+    auto emit = [&](int p, const int4& o) {
+      st_v4(y + ybase + (size_t)p * C, o);
+      if (dst_up && p < halo.w) st_v4(dst_up + (size_t)p * C, o);
+      if (dst_dn && p >= last_row0) st_v4(dst_dn + (size_t)(p - last_row0) * C, o);
+    };
+    int p = p0 + pl;
+    for (; p + 3 * lanes < p1; p += 4 * lanes) {
+      int4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = STREAM ? ld_nc_v4(x + base + (size_t)(p + u * lanes) * C) : ld_v4(x + base + (size_t)(p + u * lanes) * C);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) emit(p + u * lanes, xform(r[u]));
+    }
+    for (; p < p1; p += lanes) emit(p, xform(STREAM ? ld_nc_v4(x + base + (size_t)p * C) : ld_v4(x + base + (size_t)p * C)));
   }
-  for (; p < p1; p += lanes) st_v4(y + base + (size_t)p * C, xform(STREAM ? ld_nc_v4(x + base + (size_t)p * C) : ld_v4(x + base + (size_t)p * C)));
+  if (!halo.enabled) return;
+  // ---- boundary rows shipped: the last CTA of the grid stamps the neighbours' flags (protocol of halo_push_kernel)
+  if (halo.push) {
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned int tk = atomicAdd(halo.ticket2, 1u);
+      if (tk == gridDim.x * gridDim.y - 1) {
+        __threadfence();
+        *halo.ticket2 = 0;
+        if (halo.up >= 0) st_release_sys(halo.c.flags[halo.up] + (size_t)halo.idx * halo.c.world + halo.c.rank, pub);
+        if (halo.down >= 0) st_release_sys(halo.c.flags[halo.down] + (size_t)halo.idx * halo.c.world + halo.c.rank, pub);
+      }
+    }
+  }
+  // ---- margin rows of sample b: first chunk fills the top one, last chunk the bottom one (zeros at the image border)
+  const bool top = chunk == 0, bottom = chunk == (int)gridDim.x - 1;
+  if (!top && !bottom) return;
+  const uint32_t rd = (halo.up >= 0 || halo.down >= 0) ? halo.c.clock[1] : 0u;
+  const size_t nb = gridDim.y;
+  const int row_vec = (int)(row_el / 8);
+#pragma unroll 1
+  for (int side = 0; side < 2; ++side) {
+    if (side == 0 ? !top : !bottom) continue;
+    const int src = side == 0 ? halo.up : halo.down;
+    __half* dst = y + ((size_t)b * (halo.h + 2) + (side == 0 ? 0 : halo.h + 1)) * row_el;
+    if (src >= 0) {
+      if (halo.wait_flags && tid == 0) spin_until(halo.c.flags[halo.c.rank] + (size_t)halo.idx * halo.c.world + src, rd, halo.c.spin_timeout_ns);
+      __syncthreads();
+      // top margin = the up neighbour's LAST row (its part 1); bottom margin = the down neighbour's FIRST row (part 0)
+      const __half* from = (const __half*)slot_ptr(halo.c, halo.c.rank, rd, halo.off, halo.slot_bytes, src) +
+                           ((side == 0 ? nb : 0) + b) * row_el;
+      for (int i = tid; i < row_vec; i += blockDim.x) st_v4(dst + (size_t)i * 8, ld_v4(from + (size_t)i * 8));
+    } else {
+      const int4 zero = make_int4(0, 0, 0, 0);
+      for (int i = tid; i < row_vec; i += blockDim.x) st_v4(dst + (size_t)i * 8, zero);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
                                                        __half* __restrict__ y, const __half* __restrict__ gamma,
                                                        const __half* __restrict__ beta,
                                                        const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
-                                                       int ppc, int silu) {
-  gn_apply_body<true>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu);
+                                                       int ppc, int silu, GnHalo halo) {
+  gn_apply_body<true>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
 }
 
 // ONE launch: statistics -> grid-wide hand-over -> normalise.  Every CTA of the grid is resident at once (the host caps the
@@ -294,9 +370,11 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
                                                           __half* __restrict__ y, const __half* __restrict__ gamma,
                                                           const __half* __restrict__ beta, float2* __restrict__ partial,
                                                           const float2* __restrict__ coef, int hw, int C, int G, int V,
-                                                          int lanes, int ppc, int silu, GnExchange ex, unsigned int* gen) {
+                                                          int lanes, int ppc, int silu, GnExchange ex, unsigned int* gen,
+                                                          GnHalo halo) {
   extern __shared__ float2 ch[];
   __shared__ unsigned int my_gen;
+  pdl_wait();
   if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
   __syncthreads();
   const bool last = gn_stats_body<false>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch);
@@ -314,7 +392,7 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
     }
     __syncthreads();
   }
-  gn_apply_body<false>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu);
+  gn_apply_body<false>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
 }
 
 }  // namespace
@@ -324,10 +402,11 @@ extern "C" size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, in
   return ((size_t)b * p.nchunk * groups + (size_t)b * groups) * sizeof(float2) + 256;
 }
 
-extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
-                                const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
-                                int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
-                                uint32_t group_mask, void* scratch, void* stream) {
+namespace {
+int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
+                   const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
+                   int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
+                   uint32_t group_mask, void* scratch, void* stream, GnHalo halo) {
   DF_REQUIRE(C % 8 == 0 && C % groups == 0 && C / 8 <= 512, "df_groupnorm_fwd: unsupported channel count %d", C);
   DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)addend % 16) == 0,
              "df_groupnorm_fwd: x / y / addend must be 16-byte aligned");
@@ -339,6 +418,7 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   GnPlan p = gn_plan(b, h, w, C);
   // scratch: [ticket (256 B, zero-initialised by the caller once)] [partials] [coef]
   unsigned int* ticket = (unsigned int*)scratch;
+  halo.ticket2 = ticket + 2;
   float2* partial = (float2*)((char*)scratch + 256);
   float2* coef = partial + (size_t)b * p.nchunk * groups;
   const int hw = h * w;
@@ -363,10 +443,9 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   }
   if (p.nchunk * b <= fused_capacity && smem <= 32 * 1024) {
     unsigned int* gen = ticket + 1;
-    gn_fused_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, (__half*)y,
-                                                              (const __half*)gamma, (const __half*)beta, partial, coef, hw, C,
-                                                              groups, p.V, p.lanes, p.ppc, fuse_silu, ex, gen);
-    DF_CHECK_LAUNCH();
+    DF_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend,
+                             (__half*)y, (const __half*)gamma, (const __half*)beta, partial, (const float2*)coef, hw, C, groups, p.V,
+                             p.lanes, p.ppc, fuse_silu, ex, gen, halo));
     return 0;
   }
   gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, partial, hw, C, groups,
@@ -374,7 +453,33 @@ extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* adden
   DF_CHECK_LAUNCH();
   gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (const __half*)addend, (__half*)y,
                                                            (const __half*)gamma, (const __half*)beta, coef, hw, C, groups, p.V,
-                                                           p.lanes, p.ppc, fuse_silu);
+                                                           p.lanes, p.ppc, fuse_silu, halo);
   DF_CHECK_LAUNCH();
   return 0;
+}
+}  // namespace
+
+extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
+                                const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
+                                int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
+                                uint32_t group_mask, void* scratch, void* stream) {
+  GnHalo halo;
+  memset(&halo, 0, sizeof(halo));
+  return groupnorm_impl(comm, x, addend, y, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu, idx,
+                        tensor_off, slot_bytes, group_mask, scratch, stream, halo);
+}
+
+extern "C" int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, void* y_padded, const void* gamma,
+                                     const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
+                                     int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
+                                     uint32_t group_mask, void* scratch, int halo_idx, uint64_t halo_off,
+                                     uint64_t halo_slot_bytes, int up_rank, int down_rank, int push, int wait_flags, void* stream) {
+  DF_REQUIRE(halo_slot_bytes >= 2ull * b * w * C * 2, "df_groupnorm_halo_fwd: halo slot too small");
+  DF_REQUIRE(up_rank < comm.world && down_rank < comm.world, "df_groupnorm_halo_fwd: neighbour outside the communicator");
+  GnHalo halo;
+  memset(&halo, 0, sizeof(halo));
+  halo.enabled = 1; halo.h = h; halo.w = w; halo.up = up_rank; halo.down = down_rank; halo.push = push; halo.wait_flags = wait_flags;
+  halo.idx = halo_idx; halo.off = halo_off; halo.slot_bytes = halo_slot_bytes; halo.c = comm;
+  return groupnorm_impl(comm, x, addend, y_padded, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu,
+                        idx, tensor_off, slot_bytes, group_mask, scratch, stream, halo);
 }

@@ -115,6 +115,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
   cluster_sync_all();                                      // the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+  pdl_wait();                                              // set-up above overlapped the tail of the previous kernel
 
   if (warp == 0) {
     // =============================================================== TMA producer (both CTAs)
@@ -327,8 +328,7 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const LinearArgs
     DF_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<BN>)));
     attr_set = true;
   }
-  linear_kernel<EPI, BN><<<ctas, NTHREADS, sizeof(SmemT<BN>), st>>>(ta, tw, args);      // cluster size 2 comes from __cluster_dims__
-  DF_CHECK_LAUNCH();
+  DF_CHECK_CUDA(launch_pdl(linear_kernel<EPI, BN>, dim3(ctas), dim3(NTHREADS), sizeof(SmemT<BN>), st, ta, tw, args));   // cluster of 2: __cluster_dims__
   return 0;
 }
 

@@ -4,6 +4,8 @@ The halo rows go to the two patch neighbours only (df_halo_push, peer stores ove
 all_gather over every rank, and the padded conv input is assembled by one vectorised kernel
 (df_halo_assemble) instead of torch.stack + cat + F.pad.  The convolution itself stays a cuDNN library call
 on the NHWC padded tensor (SURVEY 8f N1 lists the hand-written implicit GEMM as a later row)."""
+import os
+
 import torch
 from torch import nn
 from torch.nn import functional as F
@@ -32,6 +34,33 @@ class DistriConv2dPP(BaseModule):
         pad_t, pad_b = max(0, -lo), max(0, hi - h)
         xs = F.pad(x[:, :, max(lo, 0):min(hi, h), :], [padding, padding, pad_t, pad_b])
         return F.conv2d(xs, self.module.weight, self.module.bias, stride=stride, padding="valid")
+
+    # -- GroupNorm-fused halo path (the producer's normalise pass writes the padded conv input, ships the boundary rows and fills
+    #    the margins: no df_halo_push / df_halo_assemble launches and no copy of the whole activation)
+    def halo_plan(self, x: torch.Tensor):
+        """-> (idx, tensor_off, slot_bytes, up, down, push) when this conv can take a padded input produced by its GroupNorm in
+        the current call, else None (one patch, first layer, buffers not created yet, not 3x3 / padding 1)."""
+        cfg = self.distri_config
+        n = cfg.n_device_per_batch
+        if n == 1 or self.is_first_layer or not self._bound() or os.environ.get("DF_FUSED_HALO", "1") == "0":
+            return None
+        m = self.module
+        if m.padding[0] != 1 or m.kernel_size[0] != 3 or m.padding[1] != 1:
+            return None
+        cm = self.comm_manager
+        r = cfg.split_idx()
+        up, down = (r - 1 if r > 0 else -1), (r + 1 if r < n - 1 else -1)
+        sync = cfg.mode == "full_sync" or self._is_sync_step()
+        push = sync or cfg.mode != "no_sync"                         # conv2d.py:92-93 / :111-112
+        return self.idx, cm.tensor_off[self.idx], cm.slot_bytes[self.idx], up, down, push
+
+    @nvtx_range("DistriConv2dPP")
+    def forward_padded(self, xp: torch.Tensor) -> torch.Tensor:
+        """xp: [b, C, h+2, w] NHWC with the halo rows in place (DistriGroupNorm.forward(..., pad_for=self))."""
+        out = F.conv2d(xp, self.module.weight, self.module.bias, stride=self.module.stride[0],
+                       padding=(0, self.module.padding[1]))          # conv2d.py:95-110
+        self.counter += 1
+        return out
 
     @nvtx_range("DistriConv2dPP")
     def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:

@@ -39,8 +39,11 @@ class DistriGroupNorm(BaseModule):
         return MODE_LOCAL, 0, 0                                      # groupnorm.py:92-93 (stock nn.GroupNorm)
 
     @nvtx_range("DistriGroupNorm")
-    def forward(self, x: torch.Tensor, addend: torch.Tensor | None = None) -> torch.Tensor:
-        """`addend` ([b, C], optional) is added to every pixel before the norm: GroupNorm(x + addend[:, :, None, None])."""
+    def forward(self, x: torch.Tensor, addend: torch.Tensor | None = None, pad_for=None) -> torch.Tensor:
+        """`addend` ([b, C], optional) is added to every pixel before the norm: GroupNorm(x + addend[:, :, None, None]).
+        `pad_for` (a DistriConv2dPP that consumes this output, optional): the result is returned as the conv's PADDED input
+        [b, C, h+2, w] with both halo rows in place (boundary rows shipped to the neighbours by the same kernel): feed it to
+        pad_for.forward_padded()."""
         module = self.module
         cfg = self.distri_config
         assert x.ndim == 4
@@ -53,7 +56,11 @@ class DistriGroupNorm(BaseModule):
             self.idx = self.comm_manager.register_tensor([2, b, G, 1, 1, 1], torch.float32, layer_type="gn")
         mode, bessel, neg_fb = self._plan()
         x = x.contiguous(memory_format=torch.channels_last)
-        y = torch.empty_like(x, memory_format=torch.channels_last)
+        halo = pad_for.halo_plan(x) if pad_for is not None else None
+        if halo is None:
+            y = torch.empty_like(x, memory_format=torch.channels_last)
+        else:
+            y = torch.empty((b, c, h + 2, w), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         L = _lib.lib()
         nbytes = L.df_groupnorm_scratch_bytes(b, G, h, w, c)
         if self._scratch is None or self._scratch.numel() < nbytes:
@@ -72,10 +79,17 @@ class DistriGroupNorm(BaseModule):
         if addend is not None:
             addend = addend.reshape(b, c).contiguous()
             assert addend.dtype == x.dtype
-        _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
-                                      mode, bessel, neg_fb, int(self.fuse_silu), self.idx or 0, off, sb, mask,
-                                      self._scratch.data_ptr(), torch.cuda.current_stream().cuda_stream),
-                   "df_groupnorm_fwd")
+        st = torch.cuda.current_stream().cuda_stream
+        if halo is None:
+            _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
+                                          mode, bessel, neg_fb, int(self.fuse_silu), self.idx or 0, off, sb, mask,
+                                          self._scratch.data_ptr(), st), "df_groupnorm_fwd")
+        else:
+            h_idx, h_off, h_sb, up, down, push = halo
+            _lib.check(L.df_groupnorm_halo_fwd(cm.group, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma,
+                                               beta, b, h, w, c, G, float(module.eps), mode, bessel, neg_fb, int(self.fuse_silu),
+                                               self.idx or 0, off, sb, mask, self._scratch.data_ptr(), h_idx, h_off, h_sb, up, down,
+                                               int(push), 1, st), "df_groupnorm_halo_fwd")
         if prof is not None:
             e1.record()
             prof.append(dict(kernel="groupnorm", kind="gn", flops=0.0, bytes=4.0 * x.numel(), shape=tuple(x.shape),

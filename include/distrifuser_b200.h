@@ -101,6 +101,18 @@ int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y,
                      int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                      uint32_t group_mask, void* scratch, void* stream);
 
+/* GroupNorm -> (SiLU) -> 3x3 conv in one pass over the activation (the ResnetBlock2D / conv_norm_out pattern): like
+ * df_groupnorm_fwd, but y_padded is [b, h+2, w, C]; the normalised rows go to rows 1..h, this rank's first / last output rows
+ * are also stored into the patch neighbours' slots of the CONV's comm tensor `halo_idx` (when push != 0; replaces
+ * df_halo_push) and rows 0 / h+1 are filled from the neighbours' slots of the read epoch, zeros at the image border (replaces
+ * df_halo_assemble and its copy of the whole activation; distrifuser/modules/pp/conv2d.py:72-93).  comm must be the patch
+ * group even when the statistics mode is 0. */
+int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, void* y_padded, const void* gamma, const void* beta,
+                          int b, int h, int w, int C, int groups, float eps, int mode, int bessel, int neg_var_fallback,
+                          int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes, uint32_t group_mask, void* scratch,
+                          int halo_idx, uint64_t halo_off, uint64_t halo_slot_bytes, int up_rank, int down_rank, int push,
+                          int wait_flags, void* stream);
+
 /* ---- conv halo exchange: replaces the boundary stack + all_gather + cat/pad of DistriConv2dPP.forward
  *      (distrifuser/modules/pp/conv2d.py:72-93).  x: [b,h,w,C] NHWC fp16, one halo row (padding 1).
  *      df_halo_push sends x's first row to patch-neighbour `up_rank` (its bottom halo) and x's last row to

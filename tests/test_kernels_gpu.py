@@ -302,6 +302,59 @@ def test_halo_push_and_assemble(up, down):
     assert ok
 
 
+@pytest.mark.parametrize("up,down", [(-1, 1), (0, 2), (2, -1)])
+@pytest.mark.parametrize("addend", [False, True])
+def test_groupnorm_fused_halo(up, down, addend):
+    """df_groupnorm_halo_fwd: GroupNorm + SiLU into the interior of the padded conv input, boundary rows shipped to the
+    neighbours' slots, margins filled from the neighbours' slots (zeros at the border) -- one kernel instead of
+    groupnorm + halo_push + halo_assemble (conv2d.py:72-93)."""
+    from distrifuser_b200 import _lib
+    L = _lib.lib()
+    torch.manual_seed(9)
+    b, c, h, w, n, G = 2, 64, 6, 10, 4, 8
+    rank = 1 if up == 0 else (0 if up < 0 else 3)
+    row_bytes = w * c * 2
+    arena = LoopbackArena(n, [b * G * 8, 2 * b * row_bytes], rank=rank)
+    x = (torch.randn(b, c, h, w, device="cuda") * 2 + 0.3).half().contiguous(memory_format=torch.channels_last)
+    t = torch.randn(b, c, device="cuda").half() if addend else None
+    gw = (1 + 0.1 * torch.randn(c, device="cuda")).half()
+    gb = (0.1 * torch.randn(c, device="cuda")).half()
+    epoch = 9
+    arena.set_clock(pub=epoch, rd=epoch)
+    top_src = torch.randn(b, w, c, device="cuda").half()
+    bot_src = torch.randn(b, w, c, device="cuda").half()
+    if up >= 0:
+        arena.slot(epoch, 1, up, 2 * b * row_bytes).view(2, b, w, c)[1].copy_(top_src)
+        arena.flags[1, up] = epoch
+    if down >= 0:
+        arena.slot(epoch, 1, down, 2 * b * row_bytes).view(2, b, w, c)[0].copy_(bot_src)
+        arena.flags[1, down] = epoch
+    yp = torch.full((b, c, h + 2, w), float("nan"), dtype=torch.float16, device="cuda").contiguous(memory_format=torch.channels_last)
+    scratch = torch.zeros(L.df_groupnorm_scratch_bytes(b, G, h, w, c), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):      # twice: the normalise-pass ticket resets itself
+        _lib.check(L.df_groupnorm_halo_fwd(arena.comm, x.data_ptr(), t.data_ptr() if addend else None, yp.data_ptr(), gw.data_ptr(),
+                                           gb.data_ptr(), b, h, w, c, G, 1e-5, 0, 0, 0, 1, 0, 0, 0, 1, scratch.data_ptr(), 1,
+                                           arena.tensor_off[1], arena.slot_bytes[1], up, down, 1, 1, st), "df_groupnorm_halo_fwd")
+    torch.cuda.synchronize()
+    xs = x.float() + (t.float()[:, :, None, None] if addend else 0.0)
+    m, m2 = _moments(xs, G)
+    ref = _gn_ref(xs, G, gw, gb, 1e-5, m, m2, bessel=False, silu=True)
+    ypn = yp.permute(0, 2, 3, 1)                     # [b, h+2, w, c] view of the NHWC memory
+    err = (ypn[:, 1:-1].float() - ref.permute(0, 2, 3, 1)).abs().max().item()
+    ok = torch.equal(ypn[:, 0], top_src if up >= 0 else torch.zeros_like(top_src))
+    ok &= torch.equal(ypn[:, -1], bot_src if down >= 0 else torch.zeros_like(bot_src))
+    mine = arena.slot(epoch, 1, rank, 2 * b * row_bytes).view(2, b, w, c)      # loopback: what this rank shipped
+    if up >= 0:
+        ok &= torch.equal(mine[0], ypn[:, 1])
+    if down >= 0:
+        ok &= torch.equal(mine[1], ypn[:, h])
+    flag = int(arena.flags[1, rank].item())
+    arena.close()
+    assert err < 6e-3, f"max abs err {err}"
+    assert ok and flag == epoch
+
+
 def test_publish_and_wait_roundtrip():
     from distrifuser_b200 import _lib
     L = _lib.lib()

@@ -18,7 +18,7 @@ EXPORTS = (
     "df_last_error", "df_version", "df_device_sm_count", "df_symm_alloc", "df_symm_open", "df_symm_close",
     "df_symm_free", "df_step_begin", "df_slot_publish", "df_slot_wait", "df_groupnorm_scratch_bytes",
     "df_groupnorm_fwd", "df_groupnorm_halo_fwd", "df_halo_push", "df_halo_assemble", "df_attn_make_kvmaps", "df_attn_workspace_bytes", "df_attn_fwd",
-    "df_output_gather", "df_geglu", "df_add_layernorm", "df_linear_supported", "df_linear_fwd",
+    "df_output_gather", "df_geglu", "df_add_layernorm", "df_linear_supported", "df_linear_geglu_block", "df_linear_fwd",
 )
 
 
@@ -66,8 +66,9 @@ def lib():
         L.df_geglu.argtypes = [vp, vp, i64, i32, i64, i64, vp]
         L.df_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, f32, vp]
         L.df_linear_supported.argtypes = [i64, i32, i32, i32]
-        L.df_linear_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, u32, u64, u64,
-                                    i32, vp]
+        L.df_linear_geglu_block.argtypes = [i64, i32, i32]
+        L.df_linear_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i64, i32, i32, i64, i64, i64, i64, i32, i32, i32, i32, i32, u32, u64,
+                                    u64, i32, vp]
         L.df_output_gather.argtypes = [DfComm, vp, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, u64, vp]
         for name in EXPORTS:
             getattr(L, name)  # AttributeError if the header and the library disagree

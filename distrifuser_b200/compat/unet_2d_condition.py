@@ -68,17 +68,17 @@ class GEGLU(nn.Module):
         self._fused = None            # (key, interleaved weight, interleaved bias) of the one-kernel projection + gate
         self.norm_fused = None        # set by BasicTransformerBlock: LayerNorm whose output feeds this projection (unused here)
 
-    def _fused_weights(self):
+    def _fused_weights(self, block):
         """Interleaved copy of proj.weight / proj.bias for the fused tcgen05 GEMM + GEGLU epilogue (ops.linear_geglu); rebuilt
-        when the source tensors change (load_state_dict, .to(), in-place edits)."""
+        when the source tensors change (load_state_dict, .to(), in-place edits) or the kernel wants another block size."""
         from .. import ops
         w, b = self.proj.weight, self.proj.bias
-        key = (w._version, w.data_ptr(), w.dtype, w.device, None if b is None else (b._version, b.data_ptr()))
+        key = (block, w._version, w.data_ptr(), w.dtype, w.device, None if b is None else (b._version, b.data_ptr()))
         if self._fused is None or self._fused[0] != key:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("GEGLU: weights changed since the last eager call; run one eager UNet call before capturing graphs")
             with torch.no_grad():
-                wi, bi = ops.geglu_interleave(w.detach(), None if b is None else b.detach())
+                wi, bi = ops.geglu_interleave(w.detach(), None if b is None else b.detach(), block)
             self._fused = (key, wi, bi)
         return self._fused[1], self._fused[2]
 
@@ -86,9 +86,10 @@ class GEGLU(nn.Module):
         if x.is_cuda and x.dtype == torch.float16:
             from .. import ops
             D, K = self.proj.out_features // 2, self.proj.in_features
-            if ops.use_fused_linear("geglu") and D % ops.GEGLU_BLOCK == 0 and ops.linear_supported(x.numel() // K, 2 * D, K, geglu=True):
-                wi, bi = self._fused_weights()
-                return ops.linear_geglu(x, wi, bi)          # projection + gate in ONE kernel: the [.., 8C] tensor never exists
+            block = ops.geglu_block(x.numel() // K, 2 * D, K) if ops.use_fused_linear("geglu") else 0
+            if block:
+                wi, bi = self._fused_weights(block)
+                return ops.linear_geglu(x, wi, bi, block)   # projection + gate in ONE kernel: the [.., 8C] tensor never exists
             return ops.geglu(self.proj(x))                  # library GEMM + one fused gate kernel
         y = self.proj(x)
         x, gate = y.chunk(2, dim=-1)

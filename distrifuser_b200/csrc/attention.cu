@@ -61,11 +61,8 @@ struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
 };
 
-#ifndef DF_PIPE_PREFETCH_AT
-#define DF_PIPE_PREFETCH_AT 2   // v4: the next sub-tile's tcgen05.ld is issued after this many of the 8 exponential groups
-#endif
 #ifndef DF_FMHA_PIPE
-#define DF_FMHA_PIPE 1       // 1: v4 software-pipelined 64-column sub-tiles; 0: v3 (whole 128-column tile per iteration)
+#define DF_FMHA_PIPE 0       // 1: v4 software-pipelined 64-column sub-tiles (experimental); 0: v3 (whole 128-column tile per iteration)
 #endif
 #ifndef DF_EMU_QUARTERS
 #define DF_EMU_QUARTERS 1    // v3: of every 4 column groups, this many take the polynomial exp2 (FMA/ALU pipes) instead of MUFU
@@ -272,17 +269,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // one sub-tile: X = its 32 S values (already in registers), Y = where the next sub-tile is prefetched
       auto sub = [&](uint32_t (&X)[32], uint32_t (&Y)[32], const int h) {
         const bool have_next = (h == 0) || (j + 1 < T);
-        // prefetch of the next sub-tile into Y (h = 0: second half of this tile; h = 1: first half of the next tile of this unit);
-        // issued after the first half of the exponentials, when half of X is dead (register cap of two CTAs per SM)
-        auto prefetch = [&]() {
-          if (h == 0) {
-            tmem_ld_16x256b_x8(lane_base + COL_S + 64, Y);
-          } else if (have_next) {
-            mbar_wait(&sm.s_full, (g + 1) & 1u);     // Q K_{j+1}^T was issued when the softmax warps released S_j (h = 0)
-            tc_fence_after();
-            tmem_ld_16x256b_x8(lane_base + COL_S, Y);
-          }
-        };
+        // prefetch of the next sub-tile into Y, issued FIRST.  h = 0: the second half of this tile -- waited for right after the
+        // row maxima below, so that S_j is released to the tensor core as early as in v3 (a late release starved the MMA warp:
+        // profiles/r2_attn_sweep_v4.txt).  h = 1: the first half of the next tile (Q K_{j+1}^T was issued at that release and is
+        // long complete); it lands under this sub-tile's exponentials and is waited for at the very end.
+        if (h == 0) {
+          tmem_ld_16x256b_x8(lane_base + COL_S + 64, Y);
+        } else if (have_next) {
+          mbar_wait(&sm.s_full, (g + 1) & 1u);
+          tc_fence_after();
+          tmem_ld_16x256b_x8(lane_base + COL_S, Y);
+        }
         const int vh = valid - 64 * h;               // valid columns of this sub-tile
         if (vh < 64) {                               // ragged last tile of a segment only (warp-uniform branch)
           asm volatile("" ::: "memory");
@@ -335,9 +332,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // does not fit the 96-register budget: ptxas spilled all of P around the store)
         {
           uint32_t pr[8];
-          exps(0, pr); exps(1, pr);
-          prefetch();
-          exps(2, pr); exps(3, pr);
+          if (h == 0) {                              // second half of S_j has landed: the tensor core may overwrite S
+            tmem_wait_ld_regs32(Y);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.s_free);
+          }
+          exps(0, pr); exps(1, pr); exps(2, pr); exps(3, pr);
           if (h == 0 && j > 0) {
             mbar_wait(&sm.pv_done, (g - 1) & 1u);    // P buffer free, O quiescent
             tc_fence_after();
@@ -381,17 +382,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         {
           uint32_t pr[8];
-          exps(4, pr); exps(5, pr);
-          if (have_next) {
-            tmem_wait_ld_regs32(Y);                  // the prefetched sub-tile has landed
-            if (h == 0) {                            // ... and with it the whole of S_j: the tensor core may overwrite S
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&sm.s_free);
-            }
-          }
-          exps(6, pr); exps(7, pr);
+          exps(4, pr); exps(5, pr); exps(6, pr); exps(7, pr);
           tmem_st_16x128b_x4(lane_base + COL_P + h * 32 + 16, pr);
+          if (h == 1 && have_next) tmem_wait_ld_regs32(Y);   // first half of S_{j+1}: in registers before the next iteration
         }
         {
           float s0, s1;

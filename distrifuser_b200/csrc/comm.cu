@@ -21,7 +21,7 @@ bool df::pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("DF_PDL");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = (e && e[0] == '1') ? 1 : 0;      // opt-in: measured neutral on a 1-GPU 1024^2 step (profiles/r2_pdl_ab.txt)
   }
   return v != 0;
 }

@@ -90,7 +90,7 @@ __device__ __forceinline__ void st_v4(void* p, const int4& v) {
 // A denoise step is a chain of ~1 400 short kernels; with the launch attribute below a kernel of this library may be scheduled
 // while its predecessor in the stream is still draining, run its prologue (TMEM / barrier set-up, tensor-map prefetch, index
 // arithmetic) and then block in pdl_wait() until the predecessor has completed and flushed its writes.  No global memory is
-// read or written before pdl_wait().  DF_PDL=0 in the environment disables the attribute (the device-side wait is then a no-op).
+// read or written before pdl_wait().  Opt-in with DF_PDL=1 (without the attribute the device-side wait is a no-op).
 bool pdl_enabled();
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

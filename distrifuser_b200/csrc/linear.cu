@@ -16,7 +16,7 @@
 // leader issues M=256 N=256 K=16 MMAs that read both CTAs' shared memory (each operand byte is fetched from L2 once per
 // pair), accumulators live in TMEM (2 x 256 columns: the epilogue of tile i overlaps the main loop of tile i+1).
 //   warp 0    TMA producer (one lane)          warp 1    MMA issuer (one lane, leader CTA only)
-//   warps 2-5 epilogue: tcgen05.ld 32 columns at a time -> bias / residual / GEGLU -> fp16 -> 16-byte global stores
+//   warps 2-9 epilogue (two per TMEM lane quarter, alternate 32-column chunks): tcgen05.ld 32 columns at a time -> bias / residual / GEGLU -> fp16 -> 16-byte global stores
 #include <math.h>
 #include <string.h>
 
@@ -32,7 +32,8 @@ constexpr int BM = 128;            // rows of A per CTA (256 per pair)
 // would leave most pairs idle (N = 1280 with M = 2048: 40 tiles on 74 pairs -> 64 tiles).  UMMA: M = 256 needs N % 16 == 0.
 constexpr int BK = 64;             // one 128-byte swizzled row of fp16
 constexpr int STAGES = 6;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue (two per TMEM lane quarter)
+constexpr int NEPI_WARPS = 8;
 constexpr uint32_t A_BYTES = BM * BK * 2;
 
 template <int BN>
@@ -103,7 +104,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&sm.tmem_full[b], 1); mbar_init(&sm.tmem_empty[b], 8); }   // 2 CTAs x 4 epilogue warps
+    for (int b = 0; b < 2; ++b) { mbar_init(&sm.tmem_full[b], 1); mbar_init(&sm.tmem_empty[b], 2 * NEPI_WARPS); }   // both CTAs' epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -160,8 +161,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       }
     }
   } else {
-    // =============================================================== epilogue (warps 2-5 of both CTAs)
+    // =============================================================== epilogue (warps 2-9 of both CTAs)
+    // warps w and w + 4 share a TMEM lane quarter (hardware: warp % 4) and take alternate 32-column chunks of the tile: with
+    // one warp per quarter the GEGLU epilogue (~40 instructions per output) took as long as the main loop of the next tile
     const int quad = warp & 3;                             // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;                     // 0: even chunks, 1: odd chunks
     const int row = quad * 32 + lane;
     const uint32_t lane_base = tmem + ((uint32_t)(quad * 32) << 16);
     const uint32_t empty_bar0 = mapa_u32(smem_u32(&sm.tmem_empty[0]), 0), empty_bar1 = mapa_u32(smem_u32(&sm.tmem_empty[1]), 0);
@@ -177,23 +181,24 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
       tc_fence_after();
       const uint32_t acc = lane_base + buf * BN;
       if (EPI == EPI_GEGLU) {
-        // accumulator columns [0,128) = hidden, [128,256) = gate of output columns [tn*128, tn*128+128)
+        // accumulator columns [0, BN/2) = hidden, [BN/2, BN) = gate of output columns [tn*BN/2, (tn+1)*BN/2); 16-column chunks
+        // (BN/2 = 80 or 128), alternate chunks per warp of a lane quarter
         const int ocol0 = tn * (BN / 2);
         __half* dst = p.out + grow * p.ldo + ocol0;
 #pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 32) {
-          uint32_t h[32], g[32];
-          tmem_ld32(acc + c, h);
-          tmem_ld32(acc + BN / 2 + c, g);
+        for (int c = chalf * 16; c < BN / 2; c += 32) {
+          uint32_t h[16], g[16];
+          tmem_ld16(acc + c, h);
+          tmem_ld16(acc + BN / 2 + c, g);
           tmem_wait_ld();
-          if (c + 32 == BN / 2) {                          // last chunk is in registers: hand the accumulator back
+          if (c + 32 >= BN / 2) {                          // this warp's last chunk is in registers: hand the accumulator back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(buf ? empty_bar1 : empty_bar0);
           }
-          if (row_ok && ocol0 + c < p.N / 2) {
+          if (row_ok) {
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < 2; ++v) {
               float bh[8], bg[8];
               if (p.bias) {
                 unpack8h(ld_v4(p.bias + tn * BN + c + v * 8), bh);
@@ -213,7 +218,7 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
                 const float2 hf = __half22float2(hh), gf = __half22float2(gg);
                 o2[j] = __floats2half2_rn(hf.x * gelu_erf(gf.x), hf.y * gelu_erf(gf.y));
               }
-              if (ocol0 + c + v * 8 < p.N / 2) st_v4(dst + c + v * 8, o);
+              st_v4(dst + c + v * 8, o);                   // N % BN == 0: every column of the tile exists
             }
           }
         }
@@ -222,11 +227,11 @@ linear_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ 
         __half* dst = p.out + grow * p.ldo + col0;
         const __half* res = p.residual ? p.residual + grow * p.ldr + col0 : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = chalf * 32; c < BN; c += 64) {
           uint32_t acc_r[32];
           tmem_ld32(acc + c, acc_r);
           tmem_wait_ld();
-          if (c + 32 == BN) {
+          if (c + 64 >= BN) {                              // this warp's last chunk
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(buf ? empty_bar1 : empty_bar0);
@@ -341,16 +346,38 @@ double tile_efficiency(int64_t M, int N, int bn, int pairs_avail) {
 
 }  // namespace
 
+namespace {
+int sm_count_cached() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  return sms;
+}
+// pair-tile width for a problem: 256, or 160 where that fills the pairs better (GEGLU: only widths that tile N exactly)
+int pick_bn(int64_t M, int N, int epilogue, int cap) {
+  const bool ok160 = epilogue == EPI_PLAIN || N % 160 == 0, ok256 = epilogue == EPI_PLAIN || N % 256 == 0;
+  if (!ok256) return ok160 ? 160 : 0;
+  if (ok160 && tile_efficiency(M, N, 160, cap) > tile_efficiency(M, N, 256, cap) + 0.02) return 160;
+  return 256;
+}
+}  // namespace
+
 extern "C" int df_linear_supported(int64_t M, int N, int K, int epilogue) {
   if (M < 1 || N < 8 || N % 8 != 0 || K < BK || K % BK != 0) return 0;
-  if (epilogue == EPI_GEGLU && N % 256 != 0) return 0;    // hidden/gate blocks of 128 must tile the interleaved weight exactly
+  if (epilogue == EPI_GEGLU && pick_bn(M, N, epilogue, sm_count_cached() / 2) == 0) return 0;   // blocks of 80 / 128 must tile N / 2
   return 1;
+}
+
+// GEGLU epilogue: rows of the interleaved weight per hidden / gate block (= half the pair-tile width chosen for this problem)
+extern "C" int df_linear_geglu_block(int64_t M, int N, int K) {
+  (void)K;
+  const int bn = pick_bn(M, N, EPI_GEGLU, sm_count_cached() / 2);
+  return bn / 2;
 }
 
 extern "C" int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const void* bias, const void* residual, void* out,
                              int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldr, int64_t ldo, int epilogue,
-                             int publish, int pub_col0, int idx, uint32_t peer_mask, uint64_t tensor_off, uint64_t slot_bytes,
-                             int max_ctas, void* stream) {
+                             int geglu_block, int publish, int pub_col0, int idx, uint32_t peer_mask, uint64_t tensor_off,
+                             uint64_t slot_bytes, int max_ctas, void* stream) {
   DF_REQUIRE(epilogue == EPI_PLAIN || epilogue == EPI_GEGLU, "df_linear_fwd: unknown epilogue %d", epilogue);
   DF_REQUIRE(df_linear_supported(M, N, K, epilogue), "df_linear_fwd: unsupported shape M=%lld N=%d K=%d (N %% 8, K %% 64%s)",
              (long long)M, N, K, epilogue == EPI_GEGLU ? ", GEGLU: N % 256" : "");
@@ -362,11 +389,14 @@ extern "C" int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const
   memset(&args, 0, sizeof(args));
   args.bias = (const __half*)bias; args.residual = (const __half*)residual; args.out = (__half*)out;
   args.M = M; args.N = N; args.K = K; args.ldr = ldr; args.ldo = ldo;
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int sms = sm_count_cached();
   const int cap = (max_ctas > 0 ? max_ctas : sms) / 2 > 0 ? (max_ctas > 0 ? max_ctas : sms) / 2 : 1;
-  int bn = 256;
-  if (epilogue == EPI_PLAIN && tile_efficiency(M, N, 160, cap) > tile_efficiency(M, N, 256, cap) + 0.02) bn = 160;
+  int bn = pick_bn(M, N, epilogue, epilogue == EPI_GEGLU ? sms / 2 : cap);   // GEGLU: must agree with df_linear_geglu_block()
+  if (epilogue == EPI_GEGLU && geglu_block > 0) {
+    DF_REQUIRE(geglu_block == 80 || geglu_block == 128, "df_linear_fwd: geglu_block must be 80 or 128");
+    bn = 2 * geglu_block;
+    DF_REQUIRE(N % bn == 0, "df_linear_fwd: interleave block %d does not tile N=%d", geglu_block, N);
+  }
   args.tiles_m = (int)((M + 2 * BM - 1) / (2 * BM));
   args.tiles_n = (N + bn - 1) / bn;
   args.publish = publish && peer_mask != 0;
@@ -384,7 +414,10 @@ extern "C" int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const
   if (int rc = make_map2d(&ta, a, M, K, lda, BM)) return rc;
   if (int rc = make_map2d(&tw, w, N, K, ldw, bn / 2)) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (epilogue == EPI_GEGLU) return launch_linear<EPI_GEGLU, 256>(ta, tw, args, 2 * pairs, st);
+  if (epilogue == EPI_GEGLU) {
+    if (bn == 160) return launch_linear<EPI_GEGLU, 160>(ta, tw, args, 2 * pairs, st);
+    return launch_linear<EPI_GEGLU, 256>(ta, tw, args, 2 * pairs, st);
+  }
   if (bn == 160) return launch_linear<EPI_PLAIN, 160>(ta, tw, args, 2 * pairs, st);
   return launch_linear<EPI_PLAIN, 256>(ta, tw, args, 2 * pairs, st);
 }

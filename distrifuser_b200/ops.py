@@ -45,24 +45,32 @@ def use_fused_linear(kind: str) -> bool:
     return kind in _FUSED_LINEAR
 
 
-GEGLU_BLOCK = 128      # rows of the interleaved GEGLU weight: [hidden block t (128 rows) | gate block t (128 rows)] per 256-row tile
+GEGLU_BLOCK = 128      # default rows of the interleaved GEGLU weight: [hidden block t | gate block t]; see geglu_block()
 
 
 def linear_supported(M: int, N: int, K: int, geglu: bool = False) -> bool:
     return bool(_lib.lib().df_linear_supported(M, N, K, 1 if geglu else 0))
 
 
-def geglu_interleave(weight: torch.Tensor, bias: torch.Tensor | None):
-    """diffusers GEGLU.proj holds [hidden (D rows) ; gate (D rows)]; the fused kernel wants them interleaved in blocks of 128
-    so that one 256-column accumulator tile carries both halves of 128 outputs."""
+def geglu_block(M: int, two_d: int, K: int) -> int:
+    """Rows per hidden / gate block the fused kernel wants for this problem (80 or 128; 0 = not supported): half of the pair-tile
+    width, chosen so that the tiles fill the 74 CTA pairs (e.g. 2048 x 10240: 256-wide tiles leave 14 % of the last round idle)."""
+    if not linear_supported(M, two_d, K, geglu=True):
+        return 0
+    return int(_lib.lib().df_linear_geglu_block(M, two_d, K))
+
+
+def geglu_interleave(weight: torch.Tensor, bias: torch.Tensor | None, block: int = GEGLU_BLOCK):
+    """diffusers GEGLU.proj holds [hidden (D rows) ; gate (D rows)]; the fused kernel wants them interleaved in blocks of `block`
+    rows so that one accumulator tile carries both halves of `block` outputs."""
     two_d, K = weight.shape
     D = two_d // 2
-    assert D % GEGLU_BLOCK == 0
-    w = torch.stack([weight[:D].reshape(D // GEGLU_BLOCK, GEGLU_BLOCK, K), weight[D:].reshape(D // GEGLU_BLOCK, GEGLU_BLOCK, K)], 1)
+    assert D % block == 0
+    w = torch.stack([weight[:D].reshape(D // block, block, K), weight[D:].reshape(D // block, block, K)], 1)
     w = w.reshape(two_d, K).contiguous()
     b = None
     if bias is not None:
-        b = torch.stack([bias[:D].reshape(-1, GEGLU_BLOCK), bias[D:].reshape(-1, GEGLU_BLOCK)], 1).reshape(two_d).contiguous()
+        b = torch.stack([bias[:D].reshape(-1, block), bias[D:].reshape(-1, block)], 1).reshape(two_d).contiguous()
     return w, b
 
 
@@ -85,14 +93,14 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor | None = No
         comm, pub_col0, idx, mask, off, sb = _lib.null_comm(), 0, 0, 0, 0, 0
     _lib.check(_lib.lib().df_linear_fwd(comm, x2.data_ptr(), weight.data_ptr(), bias.data_ptr() if bias is not None else None,
                                         r2.data_ptr() if r2 is not None else None, o2.data_ptr(), M, N, K, x2.stride(0),
-                                        weight.stride(0), r2.stride(0) if r2 is not None else 0, o2.stride(0), 0,
+                                        weight.stride(0), r2.stride(0) if r2 is not None else 0, o2.stride(0), 0, 0,
                                         int(publish is not None), pub_col0, idx, mask, off, sb, 0,
                                         torch.cuda.current_stream().cuda_stream), "df_linear_fwd")
     return out
 
 
-def linear_geglu(x: torch.Tensor, w_interleaved: torch.Tensor, b_interleaved: torch.Tensor | None) -> torch.Tensor:
-    """hidden * gelu_erf(gate) of the GEGLU projection in ONE kernel; weights from geglu_interleave()."""
+def linear_geglu(x: torch.Tensor, w_interleaved: torch.Tensor, b_interleaved: torch.Tensor | None, block: int = GEGLU_BLOCK) -> torch.Tensor:
+    """hidden * gelu_erf(gate) of the GEGLU projection in ONE kernel; weights from geglu_interleave(..., block)."""
     assert x.is_cuda and x.dtype == torch.float16 and x.stride(-1) == 1
     K = x.shape[-1]
     N = w_interleaved.shape[0]
@@ -100,6 +108,6 @@ def linear_geglu(x: torch.Tensor, w_interleaved: torch.Tensor, b_interleaved: to
     out = torch.empty((*x.shape[:-1], N // 2), dtype=x.dtype, device=x.device)
     _lib.check(_lib.lib().df_linear_fwd(_lib.null_comm(), x2.data_ptr(), w_interleaved.data_ptr(),
                                         b_interleaved.data_ptr() if b_interleaved is not None else None, None, out.data_ptr(),
-                                        x2.shape[0], N, K, x2.stride(0), w_interleaved.stride(0), 0, N // 2, 1, 0, 0, 0, 0, 0, 0, 0,
+                                        x2.shape[0], N, K, x2.stride(0), w_interleaved.stride(0), 0, N // 2, 1, block, 0, 0, 0, 0, 0, 0, 0,
                                         torch.cuda.current_stream().cuda_stream), "df_linear_fwd")
     return out

@@ -168,18 +168,21 @@ int df_add_layernorm(const void* x, const void* r, void* s_out, void* y, const v
  *      distrifuser/modules/pp/attn.py:121-125,159 and the diffusers FeedForward between the wrappers):
  *        out[M,N] = a[M,K] . w[N,K]^T (+ bias[N]) (+ residual[M,N])                         epilogue 0
  *        out[M,N/2] = (a.Wh^T + bh) * gelu_erf(a.Wg^T + bg), rows of w (and bias) interleaved in blocks of
- *                     128: [hidden block t | gate block t]  (diffusers GEGLU without its [M,8C] intermediate)   epilogue 1
- *      All matrices fp16 row-major with pitches lda / ldw / ldr / ldo in elements; N % 8 == 0, K % 64 == 0 (GEGLU: N % 256 == 0):
+ *                     80 or 128 (df_linear_geglu_block): [hidden block t | gate block t]  (diffusers GEGLU without its [M,8C] intermediate)   epilogue 1
+ *      All matrices fp16 row-major with pitches lda / ldw / ldr / ldo in elements; N % 8 == 0, K % 64 == 0 (GEGLU: N % 160 == 0 or N % 256 == 0):
  *      df_linear_supported() tells; unsupported shapes stay library calls.
  *      publish != 0 (epilogue 0 only): the columns >= pub_col0 are ALSO stored into slot(pub % NB, idx, src = comm.rank) of every
  *      member in peer_mask, row-major [M, N - pub_col0], and the peers' flags are stamped with the publish epoch -- the k|v
  *      half of the fused q|k|v projection goes straight into the peers' arenas (replaces enqueue, utils.py:181-190).
  *      max_ctas: 0 = all SMs. ------------------------------------------------------------------------------- */
 int df_linear_supported(int64_t M, int N, int K, int epilogue);
+/* rows per hidden / gate block of the interleaved GEGLU weight for this problem (80 or 128 = half the pair-tile width the
+ * kernel will use); pass the same value as `geglu_block` (0 = let the kernel pick, must then match the interleave). */
+int df_linear_geglu_block(int64_t M, int N, int K);
 int df_linear_fwd(df_comm_t comm, const void* a, const void* w, const void* bias, const void* residual, void* out,
                   int64_t M, int N, int K, int64_t lda, int64_t ldw, int64_t ldr, int64_t ldo, int epilogue,
-                  int publish, int pub_col0, int idx, uint32_t peer_mask, uint64_t tensor_off, uint64_t slot_bytes,
-                  int max_ctas, void* stream);
+                  int geglu_block, int publish, int pub_col0, int idx, uint32_t peer_mask, uint64_t tensor_off,
+                  uint64_t slot_bytes, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

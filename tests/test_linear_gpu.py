@@ -56,7 +56,7 @@ def test_linear_strided_input_and_batched_shape():
     _close(out, ref)
 
 
-@pytest.mark.parametrize("M,K,D", [(2048, 1280, 5120), (8192, 640, 2560), (3600, 1280, 5120), (200, 320, 1280)])
+@pytest.mark.parametrize("M,K,D", [(2048, 1280, 5120), (8192, 640, 2560), (3600, 1280, 5120), (200, 320, 1280), (300, 64, 128), (500, 128, 80)])
 def test_linear_geglu_fused(M, K, D):
     """diffusers GEGLU: y = proj(x); hidden, gate = y.chunk(2); hidden * gelu(gate) -- one kernel, interleaved weight."""
     from distrifuser_b200 import ops
@@ -64,8 +64,10 @@ def test_linear_geglu_fused(M, K, D):
     x = torch.randn(M, K, device="cuda").half()
     w = (torch.randn(2 * D, K, device="cuda") / K ** 0.5).half()
     b = (0.5 * torch.randn(2 * D, device="cuda")).half()
-    wi, bi = ops.geglu_interleave(w, b)
-    out = ops.linear_geglu(x, wi, bi)
+    block = ops.geglu_block(M, 2 * D, K)
+    assert block in (80, 128)
+    wi, bi = ops.geglu_interleave(w, b, block)
+    out = ops.linear_geglu(x, wi, bi, block)
     torch.cuda.synchronize()
     y = (x.float() @ w.float().t() + b.float()).half().float()      # the projection is an fp16 tensor in diffusers
     ref = y[:, :D] * torch.nn.functional.gelu(y[:, D:])

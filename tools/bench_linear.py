@@ -71,10 +71,11 @@ for name, M, K, D, count in [("l2 ff1+geglu", T2, 1280, 5120, 60), ("l1 ff1+gegl
         x = torch.randn(M, K, device="cuda").half()
         w = (torch.randn(2 * D, K, device="cuda") / K ** 0.5).half()
         bias = torch.randn(2 * D, device="cuda").half()
-        sets.append((x, w, bias) + ops.geglu_interleave(w, bias))
+        blk = ops.geglu_block(M, 2 * D, K)
+        sets.append((x, w, bias) + ops.geglu_interleave(w, bias, blk) + (blk,))
     t_two = timeit(lambda s_: (lambda: ops.geglu(F.linear(s_[0], s_[1], s_[2]))), sets)
-    t_one = timeit(lambda s_: (lambda: ops.linear_geglu(s_[0], s_[3], s_[4])), sets)
+    t_one = timeit(lambda s_: (lambda: ops.linear_geglu(s_[0], s_[3], s_[4], s_[5])), sets)
     del sets
     fl = 2.0 * M * 2 * D * K
-    print(f"{name:14s} M={M:6d} K={K:5d} D={D:5d} x{count:3d}: fused {t_one * 1e3:8.1f} us {fl / t_one / 1e9:7.1f} TFLOP/s | "
+    print(f"{name:14s} M={M:6d} K={K:5d} D={D:5d} blk={blk} x{count:3d}: fused {t_one * 1e3:8.1f} us {fl / t_one / 1e9:7.1f} TFLOP/s | "
           f"cuBLAS+geglu {t_two * 1e3:8.1f} us | x{t_two / t_one:.2f}   (saves {(t_two - t_one) * count:.3f} ms/step)")

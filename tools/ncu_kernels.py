@@ -74,8 +74,9 @@ if "linear" in which:
     x = torch.randn(M, K, device="cuda").half()
     w = (torch.randn(2 * D, K, device="cuda") / K ** 0.5).half()
     bias = torch.randn(2 * D, device="cuda").half()
-    wi, bi = ops.geglu_interleave(w, bias)
-    profiled(lambda: ops.linear_geglu(x, wi, bi))
+    blk = ops.geglu_block(M, 2 * D, K)
+    wi, bi = ops.geglu_interleave(w, bias, blk)
+    profiled(lambda: ops.linear_geglu(x, wi, bi, blk))
     h = torch.randn(M, D, device="cuda").half()
     w2 = (torch.randn(K, D, device="cuda") / D ** 0.5).half()
     b2 = torch.randn(K, device="cuda").half()

@@ -61,9 +61,6 @@ struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
 };
 
-#ifndef DF_FMHA_PIPE
-#define DF_FMHA_PIPE 0       // 1: v4 software-pipelined 64-column sub-tiles (experimental); 0: v3 (whole 128-column tile per iteration)
-#endif
 #ifndef DF_EMU_QUARTERS
 #define DF_EMU_QUARTERS 1    // v3: of every 4 column groups, this many take the polynomial exp2 (FMA/ALU pipes) instead of MUFU
 #endif
@@ -237,229 +234,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else {
     // =============================================================== softmax / correction / epilogue (warps 0-7)
-#if DF_FMHA_PIPE
-    // v4: SOFTWARE-PIPELINED softmax.  Warp w owns 16 rows (TMEM lanes 32*(w&3) + 16*(w>>2) ..+15) in the 16x256b fragment
-    // layout (thread t: rows rA = t/4, rB = t/4 + 8; a row lives in one quad -> row maxima are two shuffles).  A 128-column S tile
-    // is processed as two 64-column SUB-TILES (32 registers each).  While the exponentials of sub-tile k run on the MUFU / FMA
-    // pipes, sub-tile k+1 (the other half of this tile, or the first half of the NEXT tile) is already being loaded from TMEM
-    // and its row maximum computed, so the chain  s_full wait -> tcgen05.ld -> max -> shuffles  no longer sits between two
-    // exponential phases of a warp: with 4 such warps per scheduler the MUFU pipe stays busy (v2 / v3 measured 63 % MUFU
-    // utilisation with MUFU as the only saturable resource -- profiles/r2_attn_sweep_v3_vs_v2_persistent.txt, EMU=0 row).
-    // The exponent reference may move at either sub-tile (lazy: only when the maximum grew by > 2^8); when it moves at the second
-    // sub-tile, the first half of P -- already in TMEM with the old reference -- is rescaled in place (rare).
-    const int quad = warp & 3, hr = warp >> 2;
-    const uint32_t lane16 = (uint32_t)(quad * 32 + hr * 16);
-    const uint32_t lane_base = tmem + (lane16 << 16);
-    const int c4 = lane & 3, r8 = lane >> 2;
-    uint32_t g = 0, ui = 0;                                        // K/V tiles / work units processed so far by this CTA (barrier phases)
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-    int q0, head, bat, split, j_begin, T;
-    decode(u, q0, head, bat, split, j_begin, T);
-    float m_refA = -INFINITY, m_refB = -INFINITY;                  // exponent references of rows rA / rB (raw S units)
-    float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
-    int t = j_begin % tps;
-    uint32_t bufX[32], bufY[32];                                   // current / prefetched sub-tile (roles swap every sub-tile)
-    mbar_wait(&sm.s_full, g & 1u);
-    tc_fence_after();
-    tmem_ld_16x256b_x8(lane_base + COL_S, bufX);
-    tmem_wait_ld_regs32(bufX);
-    for (int j = 0; j < T; ++j, ++t, ++g) {
-      if (t == tps) t = 0;
-      const int valid = min(BN, lseg - t * BN);
-      // one sub-tile: X = its 32 S values (already in registers), Y = where the next sub-tile is prefetched
-      auto sub = [&](uint32_t (&X)[32], uint32_t (&Y)[32], const int h) {
-        const bool have_next = (h == 0) || (j + 1 < T);
-        // prefetch of the next sub-tile into Y, issued FIRST.  h = 0: the second half of this tile -- waited for right after the
-        // row maxima below, so that S_j is released to the tensor core as early as in v3 (a late release starved the MMA warp:
-        // profiles/r2_attn_sweep_v4.txt).  h = 1: the first half of the next tile (Q K_{j+1}^T was issued at that release and is
-        // long complete); it lands under this sub-tile's exponentials and is waited for at the very end.
-        if (h == 0) {
-          tmem_ld_16x256b_x8(lane_base + COL_S + 64, Y);
-        } else if (have_next) {
-          mbar_wait(&sm.s_full, (g + 1) & 1u);
-          tc_fence_after();
-          tmem_ld_16x256b_x8(lane_base + COL_S, Y);
-        }
-        const int vh = valid - 64 * h;               // valid columns of this sub-tile
-        if (vh < 64) {                               // ragged last tile of a segment only (warp-uniform branch)
-          asm volatile("" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              if (8 * i + 2 * c4 + k >= vh) { X[4 * i + k] = 0xff800000u; X[4 * i + 2 + k] = 0xff800000u; }
-        }
-        // ---- row maxima (two chains per row), quad reduce
-        float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          mA0 = max3(mA0, __uint_as_float(X[4 * i]), __uint_as_float(X[4 * i + 1]));
-          mB0 = max3(mB0, __uint_as_float(X[4 * i + 2]), __uint_as_float(X[4 * i + 3]));
-          mA1 = max3(mA1, __uint_as_float(X[4 * i + 4]), __uint_as_float(X[4 * i + 5]));
-          mB1 = max3(mB1, __uint_as_float(X[4 * i + 6]), __uint_as_float(X[4 * i + 7]));
-        }
-        float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
-        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
-        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
-        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
-        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-        // ---- lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
-        float alphaA = 1.f, alphaB = 1.f;
-        bool moved = false;
-        if ((mA - m_refA) * scale_log2 > 8.f) { alphaA = ex2((m_refA - mA) * scale_log2); m_refA = mA; lA *= alphaA; moved = true; }
-        if ((mB - m_refB) * scale_log2 > 8.f) { alphaB = ex2((m_refB - mB) * scale_log2); m_refB = mB; lB *= alphaB; moved = true; }
-        const float nA = -m_refA * scale_log2, nB = -m_refB * scale_log2;
-        const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
-        uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
-        auto exps = [&](const int i, uint32_t* pr) {   // pr: 8 packed-P registers of a group of 4 column blocks
-          const uint64_t xA = fma2(pack2(__uint_as_float(X[4 * i]), __uint_as_float(X[4 * i + 1])), scale2, nA2);
-          const uint64_t xB = fma2(pack2(__uint_as_float(X[4 * i + 2]), __uint_as_float(X[4 * i + 3])), scale2, nB2);
-          float a0, a1, b0, b1;
-          if ((i & 3) < DF_EMU_QUARTERS) {           // this share of the exponentials runs on the FMA / ALU pipes
-            ex2_poly2(xA, a0, a1);
-            ex2_poly2(xB, b0, b1);
-          } else {
-            float x0, x1;
-            unpack2(xA, x0, x1); a0 = ex2(x0); a1 = ex2(x1);
-            unpack2(xB, x0, x1); b0 = ex2(x0); b1 = ex2(x1);
-          }
-          sA = add2(sA, pack2(a0, a1));
-          sB = add2(sB, pack2(b0, b1));
-          pr[2 * (i & 3)] = pack_h2(a0, a1);
-          pr[2 * (i & 3) + 1] = pack_h2(b0, b1);
-        };
-        // P goes to TMEM in two stores of 8 registers per sub-tile (a 16-register block next to the two 32-register S blocks
-        // does not fit the 96-register budget: ptxas spilled all of P around the store)
-        {
-          uint32_t pr[8];
-          if (h == 0) {                              // second half of S_j has landed: the tensor core may overwrite S
-            tmem_wait_ld_regs32(Y);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.s_free);
-          }
-          exps(0, pr); exps(1, pr); exps(2, pr); exps(3, pr);
-          if (h == 0 && j > 0) {
-            mbar_wait(&sm.pv_done, (g - 1) & 1u);    // P buffer free, O quiescent
-            tc_fence_after();
-          }
-          if (__any_sync(0xffffffffu, moved)) {      // rare: 8 registers at a time, compact loops
-            if (j > 0) {                             // rescale this warp's 16 rows of O
-#pragma unroll 1
-              for (int cc = 0; cc < NBLK * HB; cc += 16) {
-                uint32_t o[8];
-                tmem_ld_16x256b_x2(lane_base + COL_O + cc, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i2 = 0; i2 < 2; ++i2) {
-                  o[4 * i2] = __float_as_uint(__uint_as_float(o[4 * i2]) * alphaA);
-                  o[4 * i2 + 1] = __float_as_uint(__uint_as_float(o[4 * i2 + 1]) * alphaA);
-                  o[4 * i2 + 2] = __float_as_uint(__uint_as_float(o[4 * i2 + 2]) * alphaB);
-                  o[4 * i2 + 3] = __float_as_uint(__uint_as_float(o[4 * i2 + 3]) * alphaB);
-                }
-                tmem_st_16x256b_x2(lane_base + COL_O + cc, o);
-              }
-            }
-            if (h == 1) {                            // first half of P_j carries the old reference: rescale it in place
-              tmem_wait_st();
-#pragma unroll 1
-              for (int cc = 0; cc < 32; cc += 8) {
-                uint32_t ph[4];
-                tmem_ld_16x128b_x2(lane_base + COL_P + cc, ph);
-                tmem_wait_ld();
-#pragma unroll
-                for (int i2 = 0; i2 < 2; ++i2) {
-                  float2 fa = __half22float2(*reinterpret_cast<__half2*>(&ph[2 * i2]));
-                  float2 fb = __half22float2(*reinterpret_cast<__half2*>(&ph[2 * i2 + 1]));
-                  ph[2 * i2] = pack_h2(fa.x * alphaA, fa.y * alphaA);
-                  ph[2 * i2 + 1] = pack_h2(fb.x * alphaB, fb.y * alphaB);
-                }
-                tmem_st_16x128b_x2(lane_base + COL_P + cc, ph);
-              }
-            }
-          }
-          tmem_st_16x128b_x4(lane_base + COL_P + h * 32, pr);
-        }
-        {
-          uint32_t pr[8];
-          exps(4, pr); exps(5, pr); exps(6, pr); exps(7, pr);
-          tmem_st_16x128b_x4(lane_base + COL_P + h * 32 + 16, pr);
-          if (h == 1 && have_next) tmem_wait_ld_regs32(Y);   // first half of S_{j+1}: in registers before the next iteration
-        }
-        {
-          float s0, s1;
-          unpack2(sA, s0, s1); lA += s0 + s1;
-          unpack2(sB, s0, s1); lB += s0 + s1;
-        }
-        if (h == 1) {
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sm.p_full);
-        }
-      };
-      sub(bufX, bufY, 0);
-      sub(bufY, bufX, 1);
-    }
-    // ---- epilogue: row sums / references -> shared memory (quad reduce), then O / l -> fp16 -> HBM in the 32x32b layout
-    //      (thread = row, 16-byte stores): warp w writes columns [32*(w>>2), +32) of the 32 rows of its lane quarter
-    lA += __shfl_xor_sync(0xffffffffu, lA, 1); lB += __shfl_xor_sync(0xffffffffu, lB, 1);
-    lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
-    if (c4 == 0) {
-      sm.red_sum[ui & 1][lane16 + r8] = lA; sm.red_sum[ui & 1][lane16 + r8 + 8] = lB;
-      sm.red_ref[ui & 1][lane16 + r8] = m_refA; sm.red_ref[ui & 1][lane16 + r8 + 8] = m_refB;
-    }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    const int half = hr;
-    const int row = quad * 32 + lane;
-    const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
-    const float l_row = sm.red_sum[ui & 1][row];        // [unit parity]: a fast warp may already be filling the next unit's sums
-    const float m_ref = sm.red_ref[ui & 1][row];
-    const float inv_l = 1.f / l_row;
-    mbar_wait(&sm.pv_done, (g - 1) & 1u);
-    tc_fence_after();
-    const int64_t prow = (((int64_t)split * (nbz / kv_splits) + bat) * heads + head) * lq + q0 + row;   // partial-result row
-    if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
-#pragma unroll
-    for (int blk = 0; blk < NBLK; ++blk) {
-      uint32_t o[32];
-      const int col0 = blk * HB + half * 32;        // first head column of this chunk
-      tmem_ld32(row_base + COL_O + col0, o);
-      tmem_wait_ld();
-      if (blk == NBLK - 1) {                        // O is in registers: the next unit's first P V may overwrite the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.o_free);
-      }
-      if (q0 + row < lq) {
-        if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
-          float* dst = part_o + prow * (NBLK * HB) + col0;
-#pragma unroll
-          for (int vq = 0; vq < 8; ++vq)
-            st_v4(dst + vq * 4, make_int4((int)o[vq * 4], (int)o[vq * 4 + 1], (int)o[vq * 4 + 2], (int)o[vq * 4 + 3]));
-        } else {
-          __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
-          const int nvec = (d - col0) / 8;          // 16-byte vectors of real (un-padded) head columns in this chunk
-#pragma unroll
-          for (int vq = 0; vq < 4; ++vq) {
-            if (vq < nvec) {
-              int4 w;
-              w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
-              w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
-              w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
-              w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
-              st_v4(dst + vq * 8, w);
-            }
-          }
-        }
-      }
-    }
-    }   // work units
-#else
     // Warp w owns 16 rows (TMEM lanes 32*(w&3) + 16*(w>>2) ..+15) and ALL 128 S columns of them, in the 16x256b fragment
     // layout: thread t holds rows rA = t/4 and rB = t/4 + 8, columns 8i + 2(t%4) + {0,1} for i = 0..15 (64 values).  A row
     // lives in one quad, so the row maximum is two shuffles -- no shared-memory exchange and no named barrier between warps
-    // (v2 split rows over two warps and paid an STS + 64-thread bar.sync + LDS per tile).
+    // (v2 split rows over two warps and paid an STS + 64-thread bar.sync + LDS per tile).  A software-pipelined variant (v4:
+    // 64-column sub-tiles, the next sub-tile's tcgen05.ld under the current exponentials) measured 25 % SLOWER -- the kernel is
+    // bound by issue slots + dependency stalls at the 96-register cap, not by the TMEM-load latency it hid
+    // (profiles/r2_attn_sweep_v4.txt) -- and was removed.
     const int quad = warp & 3, hr = warp >> 2;
     const uint32_t lane16 = (uint32_t)(quad * 32 + hr * 16);
     const uint32_t lane_base = tmem + (lane16 << 16);
@@ -629,7 +410,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
     }
     }   // work units
-#endif
   }
   tc_fence_before();
   __syncthreads();

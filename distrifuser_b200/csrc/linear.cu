@@ -337,11 +337,16 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const LinearArgs
   return 0;
 }
 
-// share of the pair-rounds x tile area that does useful work: wave quantisation x column padding
-double tile_efficiency(int64_t M, int N, int bn, int pairs_avail) {
+// Relative cost of a problem with pair tiles of width bn: rounds x cycles per 64-wide K block of one tile.  A K block costs
+// max(tensor cycles, shared-memory cycles): 2*bn cycles of M=256 MMAs against (16 KiB of A + bn*64 B of W) written by TMA AND
+// read by the tensor core through a 128 B/cycle port = 256 + bn cycles.  256-wide tiles balance the two (512 / 512); 160-wide
+// tiles are shared-memory bound (320 / 416) and only pay off when they fill many more pairs (measured: the 2048 x 10240 GEGLU
+// projection runs 49 us with 256-wide and 52 us with 160-wide tiles although the latter waste no round -- profiles/r2_linear_*).
+double tile_cost(int64_t M, int N, int bn, int pairs_avail) {
   const long long tm = (M + 2 * BM - 1) / (2 * BM), tn = (N + bn - 1) / bn, tiles = tm * tn;
   const long long rounds = (tiles + pairs_avail - 1) / pairs_avail;
-  return (double)tiles / (double)(rounds * pairs_avail) * ((double)N / (double)(tn * bn));
+  const int per_kblock = 2 * bn > 256 + bn ? 2 * bn : 256 + bn;
+  return (double)rounds * per_kblock;
 }
 
 }  // namespace
@@ -356,7 +361,7 @@ int sm_count_cached() {
 int pick_bn(int64_t M, int N, int epilogue, int cap) {
   const bool ok160 = epilogue == EPI_PLAIN || N % 160 == 0, ok256 = epilogue == EPI_PLAIN || N % 256 == 0;
   if (!ok256) return ok160 ? 160 : 0;
-  if (ok160 && tile_efficiency(M, N, 160, cap) > tile_efficiency(M, N, 256, cap) + 0.02) return 160;
+  if (ok160 && tile_cost(M, N, 160, cap) < 0.97 * tile_cost(M, N, 256, cap)) return 160;
   return 256;
 }
 }  // namespace

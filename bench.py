@@ -340,13 +340,17 @@ def attention_roofline(a, pipe, cfg, image, ms_image, dev, world, R):
         outs = [torch.empty_like(q_) for q_ in qs]
         side = torch.cuda.Stream(device=dev)
 
+        from distrifuser_b200.modules.pp.attn import _shared_workspace
+        ws_bytes = L.df_attn_workspace_bytes(bb, lq_, lkv_, 1, heads_, d_)          # same scratch (balanced-tail schedule) as in the model
+        ws_ptr = _shared_workspace(dev, ws_bytes).data_ptr() if ws_bytes else None
+
         def launch_all():
             st = torch.cuda.current_stream().cuda_stream
             for i in range(count):
                 q_, kv_, o_ = qs[i % nbuf], kvs[i % nbuf], outs[i % nbuf]
                 _lib.check(L.df_attn_fwd(_lib.null_comm(), q_.data_ptr(), kv_.data_ptr(), o_.data_ptr(), None, bb, lq_, lkv_,
-                                         heads_, d_, q_.stride(1), kv_.stride(1), o_.stride(1), 1, 0, seg, 0, 0, 0.0, None, 0,
-                                         st), "df_attn_fwd")
+                                         heads_, d_, q_.stride(1), kv_.stride(1), o_.stride(1), 1, 0, seg, 0, 0, 0.0, ws_ptr,
+                                         ws_bytes, st), "df_attn_fwd")
         with torch.cuda.stream(side):
             launch_all()
         torch.cuda.synchronize()

@@ -51,11 +51,23 @@ struct __align__(1024) SmemT {
   uint64_t pv_done;
   uint64_t o_free;            // the epilogue of the previous work unit has pulled O out of TMEM
   uint32_t tmem_base;
+  uint32_t ticket;            // arrival ticket of this part among the parts of its left-over unit
 };
 template <int NBLK> struct Cfg;
 template <> struct Cfg<1> { static constexpr int KST = 3, VST = 2, CTAS = 2; static constexpr uint32_t TMEM = 256; };
 template <> struct Cfg<2> { static constexpr int KST = 2, VST = 2, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; static constexpr uint32_t TMEM = 512; };
+
+// work schedule of one launch (host: plan_schedule): every CTA takes `a` whole units; the R left-over units are cut into P parts
+struct Sched {
+  int a, R, P;
+};
+
+__device__ __forceinline__ float2 ld_f2(const float2* p) {          // coherent load (partials were written during this launch)
+  float2 r;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+  return r;
+}
 
 struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
@@ -83,8 +95,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<NBLK>::CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
-                float scale_log2, int kv_splits, int nbz /* batch * kv_splits */, float* __restrict__ part_o,
-                float2* __restrict__ part_ml) {
+                float scale_log2, Sched sched, float* part_o, float2* part_ml, unsigned int* part_cnt) {
   constexpr int KSTAGES = Cfg<NBLK>::KST, VSTAGES = Cfg<NBLK>::VST;
   constexpr uint32_t TMEM_COLS = Cfg<NBLK>::TMEM, TILE_BYTES = NBLK * BLK_BYTES;
   using Smem = SmemT<NBLK, KSTAGES, VSTAGES>;
@@ -93,22 +104,35 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // PERSISTENT CTAs: the grid is min(#work units, resident CTA slots); CTA c walks the units c, c + gridDim.x, ...  A work unit
-  // is one 128-row Q tile of one (batch, head) -- or, with split-KV (small grids), one K/V range of it.  The roles keep their
-  // rings / barrier phases running across units (tile counter g), so the TMEM allocation, barrier set-up, tensor-map fetch and
-  // pipeline fill are paid once per CTA and the K/V loads of the next unit run under the epilogue of the current one.
+  // PERSISTENT CTAs with a BALANCED TAIL.  A work unit is one 128-row Q tile of one (batch, head).  CTA c first walks the whole
+  // units c, c + G, ... (G = gridDim.x resident CTAs); the R = n_units mod G left-over units -- which would otherwise keep R
+  // CTAs busy for a full extra round while G - R idle (320 units on 296 slots at SDXL 1024^2 level 2) -- are each cut into P
+  // K/V ranges, given to CTAs r*P + p as their last item; the parts leave un-normalised fp32 partials in the workspace and the
+  // LAST part to finish (a ticket per unit) merges them and writes the rows.  With fewer units than slots (short per-rank Q at
+  // n >= 4) every unit is "left over": the same mechanism spreads its K/V range over the idle SMs.  The roles keep their rings /
+  // barrier phases running across items (tile counter g): TMEM allocation, barrier set-up, tensor-map fetch and pipeline fill
+  // are paid once per CTA, and the K/V loads of the next item run under the epilogue of the current one.
   const int nqt = (lq + BM - 1) / BM;
   const int tps = (lseg + BN - 1) / BN;  // tiles per segment
   const int T_all = nseg * tps;
-  const int n_units = nqt * heads * nbz;
-  auto decode = [&](int u, int& q0, int& head, int& bat, int& split, int& j_begin, int& T) {
+  const int n_items = sched.a + ((int)blockIdx.x < sched.R * sched.P ? 1 : 0);
+  // item `it` of this CTA -> Q tile origin, head, batch, first K/V tile, tile count, partial slot (-1: whole unit), left-over index
+  auto get_item = [&](int it, int& q0, int& head, int& bat, int& j_begin, int& T, int& slot, int& lo) {
+    int u;
+    if (it < sched.a) {
+      u = it * (int)gridDim.x + (int)blockIdx.x; j_begin = 0; T = T_all; slot = -1; lo = -1;
+    } else {
+      lo = (int)blockIdx.x / sched.P;
+      const int part = (int)blockIdx.x - lo * sched.P;
+      u = sched.a * (int)gridDim.x + lo;
+      j_begin = (int)((long long)part * T_all / sched.P);
+      T = (int)((long long)(part + 1) * T_all / sched.P) - j_begin;     // >= 1: P <= T_all
+      slot = sched.P > 1 ? (int)blockIdx.x : -1;
+    }
     const int qt = u % nqt, rest = u / nqt;
     head = rest % heads;
-    const int z = rest / heads;
-    bat = z / kv_splits; split = z - bat * kv_splits;
+    bat = rest / heads;
     q0 = qt * BM;
-    j_begin = (int)((long long)split * T_all / kv_splits);
-    T = (int)((long long)(split + 1) * T_all / kv_splits) - j_begin;   // >= 1: kv_splits <= T_all
   };
 
   if (warp == WARP_MMA && lane == 0) {
@@ -141,10 +165,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
       uint32_t g = 0, ui = 0;                              // K/V tiles and work units issued so far by this CTA
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-        int q0, head, bat, split, j_begin, T;
-        decode(u, q0, head, bat, split, j_begin, T);
-        mbar_wait(&sm.q_empty, (ui & 1u) ^ 1u);            // every Q K^T of the previous unit has completed
+      for (int it = 0; it < n_items; ++it, ++ui) {
+        int q0, head, bat, j_begin, T, slot, lo;
+        get_item(it, q0, head, bat, j_begin, T, slot, lo);
+        mbar_wait(&sm.q_empty, (ui & 1u) ^ 1u);            // every Q K^T of the previous item has completed
         mbar_expect_tx(&sm.q_full, TILE_BYTES);
 #pragma unroll
         for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
@@ -194,9 +218,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(&sm.s_full);
       };
       uint32_t g = 0, ui = 0;                              // K/V tiles and work units consumed so far by this CTA
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-        int q0, head, bat, split, j_begin, T;
-        decode(u, q0, head, bat, split, j_begin, T);
+      for (int it = 0; it < n_items; ++it, ++ui) {
+        int q0, head, bat, j_begin, T, slot, lo;
+        get_item(it, q0, head, bat, j_begin, T, slot, lo);
         mbar_wait(&sm.q_full, ui & 1u);
         if (g > 0) {                                       // S still holds the last tile of the previous unit until the
           mbar_wait(&sm.s_free, (g - 1) & 1u);             // softmax warps have pulled it into registers
@@ -246,9 +270,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t lane_base = tmem + (lane16 << 16);
     const int c4 = lane & 3, r8 = lane >> 2;
     uint32_t g = 0, ui = 0;                                        // K/V tiles / work units processed so far by this CTA (barrier phases)
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ui) {
-    int q0, head, bat, split, j_begin, T;
-    decode(u, q0, head, bat, split, j_begin, T);
+    for (int it = 0; it < n_items; ++it, ++ui) {
+    int q0, head, bat, j_begin, T, slot, lo;
+    get_item(it, q0, head, bat, j_begin, T, slot, lo);
     float m_refA = -INFINITY, m_refB = -INFINITY;                  // exponent references of rows rA / rB (raw S units)
     float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
     int t = j_begin % tps;
@@ -370,41 +394,86 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
     const float l_row = sm.red_sum[ui & 1][row];        // [unit parity]: a fast warp may already be filling the next unit's sums
     const float m_ref = sm.red_ref[ui & 1][row];
-    const float inv_l = 1.f / l_row;
     mbar_wait(&sm.pv_done, (g - 1) & 1u);
     tc_fence_after();
-    const int64_t prow = (((int64_t)split * (nbz / kv_splits) + bat) * heads + head) * lq + q0 + row;   // partial-result row
-    if (kv_splits > 1 && half == 0 && q0 + row < lq) part_ml[prow] = make_float2(m_ref, l_row);
+    const bool partial = slot >= 0;
+    const int64_t prow = (int64_t)(partial ? slot : 0) * BM + row;          // row of this part's partial in the workspace
+    if (partial && half == 0) part_ml[prow] = make_float2(m_ref, l_row);
+    uint32_t o[NBLK][32];
 #pragma unroll
-    for (int blk = 0; blk < NBLK; ++blk) {
-      uint32_t o[32];
-      const int col0 = blk * HB + half * 32;        // first head column of this chunk
-      tmem_ld32(row_base + COL_O + col0, o);
-      tmem_wait_ld();
-      if (blk == NBLK - 1) {                        // O is in registers: the next unit's first P V may overwrite the accumulator
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.o_free);
+    for (int blk = 0; blk < NBLK; ++blk) tmem_ld32(row_base + COL_O + blk * HB + half * 32, o[blk]);
+    tmem_wait_ld();
+    tc_fence_before();                                // O is in registers: the next item's first P V may overwrite the accumulator
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.o_free);
+    bool finish = !partial;                           // this CTA writes the output rows
+    float m_all = m_ref, denom = l_row, w_own = 1.f;
+    if (partial) {
+      // ---- un-normalised fp32 partial (reference max m_ref) -> workspace; the last part of this unit to arrive merges
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        float* dst = part_o + prow * (NBLK * HB) + blk * HB + half * 32;
+#pragma unroll
+        for (int vq = 0; vq < 8; ++vq)
+          st_v4(dst + vq * 4, make_int4((int)o[blk][vq * 4], (int)o[blk][vq * 4 + 1], (int)o[blk][vq * 4 + 2], (int)o[blk][vq * 4 + 3]));
       }
-      if (q0 + row < lq) {
-        if (kv_splits > 1) {                        // un-normalised fp32 partial, reference max m_ref; df::combine finishes
-          float* dst = part_o + prow * (NBLK * HB) + col0;
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 0) {
+        const unsigned int tk = atomicAdd(part_cnt + lo, 1u);
+        sm.ticket = tk;
+        if (tk == (unsigned int)sched.P - 1) part_cnt[lo] = 0;        // self-resetting: the next launch is stream-ordered
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      finish = sm.ticket == (unsigned int)sched.P - 1;
+      if (finish) {
+        __threadfence();
+        // merge: out = sum_p w_p O_p / sum_p w_p l_p,  w_p = 2^((m_p - max_p m_p) * scale)   (parts of unit `lo`: slots lo*P ..)
+        const int s0 = lo * sched.P;
+        float m_max = -INFINITY;
+        for (int pp = 0; pp < sched.P; ++pp) m_max = fmaxf(m_max, ld_f2(part_ml + (int64_t)(s0 + pp) * BM + row).x);
+        m_all = m_max;
+        denom = 0.f;
 #pragma unroll
-          for (int vq = 0; vq < 8; ++vq)
-            st_v4(dst + vq * 4, make_int4((int)o[vq * 4], (int)o[vq * 4 + 1], (int)o[vq * 4 + 2], (int)o[vq * 4 + 3]));
-        } else {
-          __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
-          const int nvec = (d - col0) / 8;          // 16-byte vectors of real (un-padded) head columns in this chunk
+        for (int blk = 0; blk < NBLK; ++blk)
 #pragma unroll
-          for (int vq = 0; vq < 4; ++vq) {
-            if (vq < nvec) {
-              int4 w;
-              w.x = pack_h2(__uint_as_float(o[vq * 8 + 0]) * inv_l, __uint_as_float(o[vq * 8 + 1]) * inv_l);
-              w.y = pack_h2(__uint_as_float(o[vq * 8 + 2]) * inv_l, __uint_as_float(o[vq * 8 + 3]) * inv_l);
-              w.z = pack_h2(__uint_as_float(o[vq * 8 + 4]) * inv_l, __uint_as_float(o[vq * 8 + 5]) * inv_l);
-              w.w = pack_h2(__uint_as_float(o[vq * 8 + 6]) * inv_l, __uint_as_float(o[vq * 8 + 7]) * inv_l);
-              st_v4(dst + vq * 8, w);
+          for (int c = 0; c < 32; ++c) o[blk][c] = 0u;
+        for (int pp = 0; pp < sched.P; ++pp) {
+          const float2 ml = ld_f2(part_ml + (int64_t)(s0 + pp) * BM + row);
+          const float w = ex2((ml.x - m_max) * scale_log2);
+          denom = fmaf(w, ml.y, denom);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) {
+            const float* src = part_o + ((int64_t)(s0 + pp) * BM + row) * (NBLK * HB) + blk * HB + half * 32;
+#pragma unroll
+            for (int vq = 0; vq < 8; ++vq) {
+              const int4 v = ld_v4(src + vq * 4);
+              o[blk][vq * 4 + 0] = __float_as_uint(fmaf(w, __int_as_float(v.x), __uint_as_float(o[blk][vq * 4 + 0])));
+              o[blk][vq * 4 + 1] = __float_as_uint(fmaf(w, __int_as_float(v.y), __uint_as_float(o[blk][vq * 4 + 1])));
+              o[blk][vq * 4 + 2] = __float_as_uint(fmaf(w, __int_as_float(v.z), __uint_as_float(o[blk][vq * 4 + 2])));
+              o[blk][vq * 4 + 3] = __float_as_uint(fmaf(w, __int_as_float(v.w), __uint_as_float(o[blk][vq * 4 + 3])));
             }
+          }
+        }
+      }
+    }
+    (void)m_all; (void)w_own;
+    if (finish && q0 + row < lq) {
+      const float inv = 1.f / denom;
+#pragma unroll
+      for (int blk = 0; blk < NBLK; ++blk) {
+        const int col0 = blk * HB + half * 32;        // first head column of this chunk
+        __half* dst = out + ((int64_t)bat * lq + q0 + row) * o_pitch + (int64_t)head * d + col0;
+        const int nvec = (d - col0) / 8;              // 16-byte vectors of real (un-padded) head columns in this chunk
+#pragma unroll
+        for (int vq = 0; vq < 4; ++vq) {
+          if (vq < nvec) {
+            int4 w;
+            w.x = pack_h2(__uint_as_float(o[blk][vq * 8 + 0]) * inv, __uint_as_float(o[blk][vq * 8 + 1]) * inv);
+            w.y = pack_h2(__uint_as_float(o[blk][vq * 8 + 2]) * inv, __uint_as_float(o[blk][vq * 8 + 3]) * inv);
+            w.z = pack_h2(__uint_as_float(o[blk][vq * 8 + 4]) * inv, __uint_as_float(o[blk][vq * 8 + 5]) * inv);
+            w.w = pack_h2(__uint_as_float(o[blk][vq * 8 + 6]) * inv, __uint_as_float(o[blk][vq * 8 + 7]) * inv);
+            st_v4(dst + vq * 8, w);
           }
         }
       }
@@ -418,33 +487,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   }
 }
 
-
-// Combine the split-KV partials: out = sum_s w_s O_s / sum_s w_s l_s with w_s = 2^((m_s - max_s m_s) * scale_log2).
-// One warp per (batch, head, q-row); lanes stride over the head columns.
-__global__ void __launch_bounds__(256) fmha_combine_kernel(const float* __restrict__ part_o, const float2* __restrict__ part_ml,
-                                                           __half* __restrict__ out, int64_t rows_per_split, int lq, int heads,
-                                                           int d, int hd_pad, int64_t o_pitch, int kv_splits, float scale_log2) {
-  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (bat * heads + head) * lq + q
-  if (r >= rows_per_split) return;
-  const int lane = threadIdx.x & 31;
-  float m = -INFINITY;
-  for (int s = 0; s < kv_splits; ++s) m = fmaxf(m, part_ml[s * rows_per_split + r].x);
-  float w[8], denom = 0.f;
-  for (int s = 0; s < kv_splits; ++s) {
-    const float2 ml = part_ml[s * rows_per_split + r];
-    w[s] = ex2((ml.x - m) * scale_log2);
-    denom = fmaf(w[s], ml.y, denom);
-  }
-  const float inv = 1.f / denom;
-  const int64_t bh = r / lq, q = r - bh * lq;
-  const int64_t bat = bh / heads, head = bh - bat * heads;
-  __half* dst = out + (bat * lq + q) * o_pitch + head * d;
-  for (int c = lane; c < d; c += 32) {
-    float acc = 0.f;
-    for (int s = 0; s < kv_splits; ++s) acc = fmaf(w[s], part_o[(s * rows_per_split + r) * hd_pad + c], acc);
-    dst[c] = __float2half_rn(acc * inv);
-  }
-}
 
 // ----------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -501,11 +543,7 @@ extern "C" int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t
 }
 
 namespace {
-// How many CTAs share the K/V range of one (batch, head, q-tile).  Measured (tools/bench_attn.py --no-split): for the short
-// K/V ranges of SDXL at 1024^2 (8-32 tiles) the extra combine launch costs more than the split saves (23.6 vs 18.4 us at
-// b=1, Lq=256, Lkv=1024), so the split is reserved for grids that fill < 1/4 of the resident CTA slots AND keep >= 8 tiles
-// per CTA (long K/V, very short Q).
-int plan_kv_splits(int b, int lq, int lseg, int nseg, int heads, int d) {
+int sm_count() {
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -513,15 +551,42 @@ int plan_kv_splits(int b, int lq, int lseg, int nseg, int heads, int d) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
+  return sms;
+}
+#ifndef DF_MIN_PART_TILES
+#define DF_MIN_PART_TILES 2    // a part of a left-over unit keeps at least this many K/V tiles (Q load + partial write + merge per part)
+#endif
+// Grid and work schedule of a launch (see the kernel): G resident CTAs, `a` whole units per CTA, R left-over units in P parts.
+void plan_schedule(int b, int lq, int lseg, int nseg, int heads, int d, bool allow_split, int& grid, Sched& sc) {
   const int nblk = (d + HB - 1) / HB;
-  const long long slots = (long long)sms * (nblk == 1 ? 2 : 1);
-  const long long ctas = (long long)((lq + BM - 1) / BM) * heads * b;
+  const long long slots = (long long)sm_count() * (nblk == 1 ? Cfg<1>::CTAS : 1);
+  const long long units = (long long)((lq + BM - 1) / BM) * heads * b;
   const int t_all = nseg * ((lseg + BN - 1) / BN);
-  if (ctas * 4 > slots || t_all < 16) return 1;
-  long long s = slots / ctas;
-  if (s > 8) s = 8;
-  if (s > t_all / 8) s = t_all / 8;
-  return s < 2 ? 1 : (int)s;
+  int max_p = allow_split ? t_all / DF_MIN_PART_TILES : 1;
+  if (max_p < 1) max_p = 1;
+  if (units >= slots) {
+    grid = (int)slots;
+    sc.a = (int)(units / slots);
+    sc.R = (int)(units % slots);
+    sc.P = 1;
+    if (sc.R > 0) {
+      long long p = slots / sc.R;
+      if (p > max_p) p = max_p;
+      sc.P = (int)(p < 1 ? 1 : p);
+    }
+  } else {
+    long long p = slots / units;
+    if (p > max_p) p = max_p;
+    if (p < 1) p = 1;
+    sc.a = 0; sc.R = (int)units; sc.P = (int)p;
+    grid = (int)(units * p);
+  }
+}
+size_t workspace_need(const Sched& sc, int d) {
+  if (sc.P <= 1) return 0;
+  const size_t hd_pad = (size_t)((d + HB - 1) / HB) * HB;
+  const size_t parts = (size_t)sc.R * sc.P;
+  return 1024 + ((size_t)sc.R * sizeof(unsigned int) + 255) / 256 * 256 + parts * BM * sizeof(float2) + parts * BM * hd_pad * sizeof(float);
 }
 }  // namespace
 
@@ -534,10 +599,10 @@ extern "C" int df_debug_read_trace(long long* out_host /* 64*16 */) {
 #endif
 
 extern "C" size_t df_attn_workspace_bytes(int b, int lq, int lseg, int nseg, int heads, int d) {
-  const int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
-  if (splits == 1) return 0;
-  const int hd_pad = ((d + HB - 1) / HB) * HB;
-  return (size_t)splits * b * heads * lq * ((size_t)hd_pad * sizeof(float) + sizeof(float2)) + 256;
+  int grid;
+  Sched sc;
+  plan_schedule(b, lq, lseg, nseg, heads, d, true, grid, sc);
+  return workspace_need(sc, d);
 }
 
 extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps, int b, int lq,
@@ -558,18 +623,25 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
   const float sc = (scale > 0.f ? scale : 1.f / sqrtf((float)d)) * 1.4426950408889634f;
   const int nblk = (d + HB - 1) / HB;
-  int splits = plan_kv_splits(b, lq, lseg, nseg, heads, d);
-  if (splits > 1 && (workspace == nullptr || workspace_bytes < df_attn_workspace_bytes(b, lq, lseg, nseg, heads, d))) splits = 1;
-  const int64_t rows = (int64_t)b * heads * lq;
-  float2* part_ml = (float2*)workspace;                                   // [splits][rows]
-  float* part_o = splits > 1 ? (float*)((char*)workspace + (((size_t)splits * rows * sizeof(float2) + 255) / 256) * 256) : nullptr;
-  // persistent CTAs: one per resident slot (2 per SM for d <= 64, else 1), each walking the work units round-robin
-  static int sm_count = 0;
-  if (!sm_count) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); if (sm_count <= 0) sm_count = 148; }
-  const long long n_units = (long long)((lq + BM - 1) / BM) * heads * b * splits;
-  DF_REQUIRE(n_units < (1ll << 31), "df_attn_fwd: too many work units");
-  const long long slots = (long long)sm_count * (nblk == 1 ? Cfg<1>::CTAS : 1);
-  dim3 grid((unsigned)(n_units < slots ? n_units : slots), 1, 1);
+  // work schedule; the left-over split needs a ZERO-INITIALISED workspace of df_attn_workspace_bytes() (it holds the self-resetting
+  // arrival tickets); without one the left-over units are processed whole
+  int grid_x;
+  Sched sched;
+  plan_schedule(b, lq, lseg, nseg, heads, d, true, grid_x, sched);
+  if (sched.P > 1 && (workspace == nullptr || workspace_bytes < workspace_need(sched, d)))
+    plan_schedule(b, lq, lseg, nseg, heads, d, false, grid_x, sched);
+  unsigned int* part_cnt = nullptr;
+  float2* part_ml = nullptr;
+  float* part_o = nullptr;
+  if (sched.P > 1) {
+    char* w = (char*)workspace;
+    part_cnt = (unsigned int*)w;
+    w += ((size_t)sched.R * sizeof(unsigned int) + 255) / 256 * 256;
+    part_ml = (float2*)w;
+    w += (size_t)sched.R * sched.P * BM * sizeof(float2);
+    part_o = (float*)(((uintptr_t)w + 255) / 256 * 256);
+  }
+  dim3 grid((unsigned)grid_x, 1, 1);
 #define DF_LAUNCH_FMHA(NB)                                                                                                  \
   {                                                                                                                          \
     static bool attr_set = false;                                                                                            \
@@ -580,16 +652,10 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
     }                                                                                                                        \
     DF_CHECK_CUDA(launch_pdl(fmha_fwd_kernel<NB>, grid, dim3(NTHREADS), smem_bytes, (cudaStream_t)stream, tq, tkv,           \
                              (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg,        \
-                             own_seg, idx, wait_flags, sc, splits, b * splits, part_o, part_ml));                            \
+                             own_seg, idx, wait_flags, sc, sched, part_o, part_ml, part_cnt));                               \
   }
   if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA
-  DF_CHECK_LAUNCH();
-  if (splits > 1) {
-    const unsigned cg = (unsigned)((rows + 7) / 8);
-    fmha_combine_kernel<<<cg, 256, 0, (cudaStream_t)stream>>>(part_o, part_ml, (__half*)out, rows, lq, heads, d, nblk * HB, o_pitch,
-                                                              splits, sc);
-  }
   DF_CHECK_LAUNCH();
   return 0;
 }

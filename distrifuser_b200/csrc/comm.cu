@@ -107,16 +107,21 @@ __device__ __forceinline__ void signal_when_last(const df_comm_t& c, int idx, ui
   }
 }
 
-// 128 threads x <= 32 registers: a publication CTA fits next to two resident attention CTAs (2 x 320 threads x 96 regs =
-// 61 440 of the 65 536 registers) instead of displacing one of them for the whole transfer.
-__global__ void __launch_bounds__(128, 16) publish_kernel(df_comm_t c, const char* __restrict__ src, uint64_t rows,
+// 128 threads, DF_PUB_UNROLL 16-byte loads in flight per thread: the transfer is bound by how many loads are outstanding (local
+// read latency ~1 us; the peer stores are posted), so few CTAs with deep unrolling move the same bytes as many shallow ones
+// while taking fewer SM slots away from the GEMM / attention kernels they run next to (exposed communication of an
+// asynchronous step, profiles/r2_exposed_comm_*.txt).
+#ifndef DF_PUB_UNROLL
+#define DF_PUB_UNROLL 8
+#endif
+__global__ void __launch_bounds__(128, 8) publish_kernel(df_comm_t c, const char* __restrict__ src, uint64_t rows,
                                                           uint64_t vec_per_row, uint64_t src_pitch, uint64_t tensor_off,
                                                           uint64_t slot_bytes, int idx, uint32_t peer_mask) {
   const uint32_t epoch = c.clock[0];
   const uint64_t total = rows * vec_per_row;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t bank_off = (uint64_t)(epoch % DF_NBANKS) * c.bank_stride + tensor_off + (uint64_t)c.rank * slot_bytes;
-  constexpr int U = 2;
+  constexpr int U = DF_PUB_UNROLL;
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (; i + (U - 1) * stride < total; i += U * stride) {
     int4 v[U];

@@ -15,6 +15,20 @@ from ...utils import DistriConfig
 from ..base_module import BaseModule, nvtx_range
 
 
+_WORKSPACES: dict = {}      # device -> list of zero-initialised scratch tensors (kept alive: captured graphs hold raw pointers)
+
+
+def _shared_workspace(device, nbytes: int) -> torch.Tensor:
+    """Scratch of the balanced-tail attention schedule (fp32 partials + self-resetting arrival tickets, df_attn_workspace_bytes).
+    One buffer per device serves every attention layer: the launches are ordered on one stream.  It must start zeroed."""
+    lst = _WORKSPACES.setdefault(device, [])
+    if not lst or lst[-1].numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("attention workspace would grow during CUDA-graph capture; run one eager UNet call first")
+        lst.append(torch.zeros(max(nbytes, 16 << 20), dtype=torch.uint8, device=device))
+    return lst[-1]
+
+
 class DistriAttentionPP(BaseModule):
     def __init__(self, module: nn.Module, distri_config: DistriConfig):
         super().__init__(module, distri_config)
@@ -33,7 +47,6 @@ class DistriAttentionPP(BaseModule):
                 to_kv.bias[out_size:].copy_(to_v.bias)
         self.to_kv = to_kv
         self._kvmaps = None
-        self._workspace = None           # split-KV scratch for small per-rank grids (df_attn_workspace_bytes)
 
     def _attend(self, q, kv_own, lseg, nseg, own_seg, wait_flags, kind="self"):
         """softmax(q k^T / sqrt(d)) v over `nseg` K/V segments of `lseg` rows each; q:[b,lq,C], kv_own:[b,lseg,2C]."""
@@ -50,9 +63,7 @@ class DistriAttentionPP(BaseModule):
         seg_rank = (C.c_int32 * _lib.MAX_WORLD)(*range(_lib.MAX_WORLD))
         L = _lib.lib()
         ws_bytes = L.df_attn_workspace_bytes(b, lq, lseg, nseg, heads, d)
-        if ws_bytes and (self._workspace is None or self._workspace.numel() < ws_bytes):
-            self._workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=q.device)
-        ws = self._workspace.data_ptr() if ws_bytes else None
+        ws = _shared_workspace(q.device, ws_bytes).data_ptr() if ws_bytes else None
         prof = _lib.PROFILE
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -20,7 +20,7 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     seg_rank = (C.c_int32 * 8)(*range(8))
     L = _lib.lib()
     ws_bytes = L.df_attn_workspace_bytes(b, lq, lseg or kv.shape[1], nseg, heads, d)      # > 0: the split-KV path is taken
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+    ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
     _lib.check(L.df_attn_fwd(comm or _lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), maps, b, lq,
                              lseg or kv.shape[1], heads, d, q.stride(1), kv.stride(1), out.stride(1), nseg, own,
                              seg_rank, idx, wait, 0.0, ws.data_ptr() if ws_bytes else None, ws_bytes,
@@ -47,6 +47,10 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (2, 2048, 300, 20, 64),        # persistent CTAs: 640 units x 3 tiles, ragged last tile
     (2, 1100, 520, 8, 80),         # persistent CTAs, two head blocks, one CTA per SM: 144 units (< 148) and ragged q
     (2, 2304, 260, 8, 160),        # persistent CTAs, three head blocks: 288 units on 148 CTAs
+    (2, 1024, 1024, 20, 64),       # SDXL 1024^2 level 2: 320 units on 296 CTAs -> 24 left-over units in 4 parts, merged in-kernel
+    (2, 4096, 1024, 10, 64),       # 640 units: two whole units per CTA + 48 left-over units in parts
+    (1, 256, 1024, 20, 64),        # SDXL 1024^2 n=4 level 2: 40 units spread over the idle SMs (every unit is "left over")
+    (1, 200, 2000, 3, 80),         # left-over parts with two head blocks, ragged q and k/v
 ])
 def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)
@@ -59,13 +63,14 @@ def test_attention_single_segment(b, lq, lk, heads, d):
     assert err < 2e-3, f"max abs err {err}"
 
 
-def test_attention_split_kv_is_planned_for_small_grids():
+def test_attention_tail_split_is_planned():
+    """df_attn_workspace_bytes > 0 exactly when the schedule cuts left-over units into K/V parts."""
     from distrifuser_b200 import _lib
     L = _lib.lib()
-    assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > 0         # 8 CTAs on 296 slots, 64 K/V tiles
-    assert L.df_attn_workspace_bytes(1, 256, 1024, 1, 20, 64) == 0       # short K/V: the combine launch would cost more
-    assert L.df_attn_workspace_bytes(2, 4096, 4096, 1, 10, 64) == 0      # 640 CTAs: single pass
-    assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile
+    assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > 0         # 8 units on 296 slots, 64 K/V tiles
+    assert L.df_attn_workspace_bytes(2, 1024, 1024, 1, 20, 64) > 0       # 320 units: 24 left over
+    assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile, nothing to cut
+    assert L.df_attn_workspace_bytes(1, 3600, 3600, 4, 20, 64) == 0      # 580 units: 284 left over on 296 slots -> whole
 
 
 def test_attention_large_logits_rescale():

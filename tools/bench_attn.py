@@ -46,7 +46,7 @@ def main():
         kvs = [torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16) for _ in range(n)]
         outs = [torch.empty_like(q) for q in qs]
         ws_bytes = 0 if a.no_split else L.df_attn_workspace_bytes(b, lq, lk, 1, h, d)
-        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+        ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
 
         def run(i=0):
             st = torch.cuda.current_stream().cuda_stream

@@ -41,9 +41,12 @@ for name, (b, lq, lk, h, d) in {"1024^2 level1": (2, 4096, 4096, 10, 64), "1024^
     seg = (C.c_int32 * 8)(*range(8))
     st = torch.cuda.current_stream().cuda_stream
 
+    ws_bytes = L.df_attn_workspace_bytes(b, lq, lk, 1, h, d)
+    ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
+
     def ours():
         _lib.check(L.df_attn_fwd(_lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), None, b, lq, lk, h, d, q.stride(1),
-                                 kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0, None, 0, st), "attn")
+                                 kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0, ws.data_ptr() if ws_bytes else None, ws_bytes, st), "attn")
     qh = q.view(b, lq, h, d).transpose(1, 2)
     kh = kv[..., :Cq].reshape(b, lk, h, d).transpose(1, 2)
     vh = kv[..., Cq:].reshape(b, lk, h, d).transpose(1, 2)

@@ -38,8 +38,11 @@ if "attn" in which:
         kv = torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16)
         out = torch.empty_like(q)
         seg = (C.c_int32 * 8)(*range(8))
+        ws_bytes = L.df_attn_workspace_bytes(b, lq, lk, 1, h, d)
+        ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
         profiled(lambda: _lib.check(L.df_attn_fwd(_lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), None, b, lq, lk, h, d,
-                                                  q.stride(1), kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0, None, 0, st), "attn"))
+                                                  q.stride(1), kv.stride(1), out.stride(1), 1, 0, seg, 0, 0, 0.0,
+                                                  ws.data_ptr() if ws_bytes else None, ws_bytes, st), "attn"))
 if "gn" in which:
     for (Cc, hh, ww) in [(320, 128, 128), (640, 64, 64), (1280, 32, 32)]:
         b, G = 2, 32

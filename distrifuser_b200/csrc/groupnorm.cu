@@ -76,7 +76,8 @@ struct GnHalo {
   df_comm_t c;
 };
 
-__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine);
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine, bool defer_publish);
+__device__ void gn_publish_async(const GnExchange& e, const float2* mine);
 
 // Statistics pass of one CTA; returns true in the LAST CTA of the grid after it has run the exchange and written coef[].
 // STREAM = true: loads bypass L1 (two-kernel path: the data is touched once); false: default caching, so that the apply pass
@@ -84,7 +85,7 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
 template <bool STREAM>
 __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, const __half* __restrict__ addend,
                                               float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
-                                              int ppc, const GnExchange& ex, float2* ch) {
+                                              int ppc, const GnExchange& ex, float2* ch, bool defer_publish = false) {
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int tid = threadIdx.x;
   const int v = tid % V, pl = tid / V;
@@ -152,7 +153,7 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
-  gn_exchange(ex, partial, G, nchunk, ch);
+  gn_exchange(ex, partial, G, nchunk, ch, defer_publish);
   return true;
 }
 
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
-__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine) {
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine, bool defer_publish) {
   const df_comm_t& c = e.c;
   float2* __restrict__ coef = e.coef;
   const int bG = e.bG, mode = e.mode, neg_fb = e.neg_fb, idx = e.idx;
@@ -237,7 +238,24 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
     var *= bessel;                                                                              // :65-66
     coef[i] = make_float2(mean, rsqrtf(var + eps));
   }
-  if (mode >= 2) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
+  if (mode >= 2 && !defer_publish) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
+}
+
+// Asynchronous modes: this step's local statistics (still in `mine`, shared memory) go to the peers' slots of the publish epoch
+// for the NEXT step.  Separate from gn_exchange so that the fused kernel can release the normalise pass first: the peer stores,
+// the system-scope fence and the flag stamps (a few microseconds over NVLink) then run beside it instead of in front of it.
+__device__ void gn_publish_async(const GnExchange& e, const float2* mine) {
+  const df_comm_t& c = e.c;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const uint32_t pub = c.clock[0];
+  for (int p = 0; p < c.world; ++p) {
+    if (!(e.group_mask >> p & 1)) continue;
+    float2* dst = (float2*)slot_ptr(c, p, pub, e.tensor_off, e.slot_bytes, c.rank);
+    for (int i = tid; i < e.bG; i += nthr) dst[i] = mine[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid < c.world && (e.group_mask >> tid & 1)) st_release_sys(c.flags[tid] + (size_t)e.idx * c.world + c.rank, pub);
 }
 
 template <bool STREAM>
@@ -377,11 +395,12 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
   pdl_wait();
   if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
   __syncthreads();
-  const bool last = gn_stats_body<false>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch);
+  const bool last = gn_stats_body<false>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
   if (last) {
     __threadfence();                                     // coef[] (written by this CTA's threads) before the generation bump
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(my_gen + 1u) : "memory");
+    if (ex.mode >= 2) gn_publish_async(ex, ch);          // the other CTAs are normalising already
   } else {
     if (threadIdx.x == 0) {
       unsigned int v;

@@ -104,12 +104,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need a 1 KiB aligned base
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // PERSISTENT CTAs with a BALANCED TAIL.  A work unit is one 128-row Q tile of one (batch, head).  CTA c first walks the whole
-  // units c, c + G, ... (G = gridDim.x resident CTAs); the R = n_units mod G left-over units -- which would otherwise keep R
-  // CTAs busy for a full extra round while G - R idle (320 units on 296 slots at SDXL 1024^2 level 2) -- are each cut into P
-  // K/V ranges, given to CTAs r*P + p as their last item; the parts leave un-normalised fp32 partials in the workspace and the
-  // LAST part to finish (a ticket per unit) merges them and writes the rows.  With fewer units than slots (short per-rank Q at
-  // n >= 4) every unit is "left over": the same mechanism spreads its K/V range over the idle SMs.  The roles keep their rings /
+  // PERSISTENT CTAs.  A work unit is one 128-row Q tile of one (batch, head).  CTA c walks the whole units c, c + G, ...
+  // (G = gridDim.x resident CTAs) and then, if c < R*P, one more item: part (c mod P) of left-over unit (c div P).  With P = 1
+  // the left-over units are simply whole units of the last round.  With P > 1 (grids that leave most SMs idle: short per-rank Q
+  // at n >= 4 with long K/V) a unit's K/V range is cut into P parts that run on otherwise idle SMs; the parts leave
+  // un-normalised fp32 partials in the workspace and the LAST part to finish (a ticket per unit) merges them and writes the rows
+  // -- no second kernel.  The roles keep their rings /
   // barrier phases running across items (tile counter g): TMEM allocation, barrier set-up, tensor-map fetch and pipeline fill
   // are paid once per CTA, and the K/V loads of the next item run under the epilogue of the current one.
   const int nqt = (lq + BM - 1) / BM;
@@ -554,29 +554,26 @@ int sm_count() {
   return sms;
 }
 #ifndef DF_MIN_PART_TILES
-#define DF_MIN_PART_TILES 2    // a part of a left-over unit keeps at least this many K/V tiles (Q load + partial write + merge per part)
+#define DF_MIN_PART_TILES 8    // a part of a split unit keeps at least this many K/V tiles (Q load + partial write + merge per part)
 #endif
 // Grid and work schedule of a launch (see the kernel): G resident CTAs, `a` whole units per CTA, R left-over units in P parts.
+// Measured policy (profiles/r2_attn_tail_split.txt): cutting the left-over units of a grid that already fills the SMs does
+// not pay -- the R CTAs of the last round have their SMs to themselves and run ~1.6x faster per tile, which a balanced tail
+// trades for partial writes and a merge (SDXL 1024^2: level 1 144 vs 136 us, level 2 32.5 vs 30.4 us) -- so P > 1 only when the
+// units leave at least half of the CTA slots idle AND every part keeps >= 8 K/V tiles (n = 4 level 1: 41.6 -> 37.7 us).
 void plan_schedule(int b, int lq, int lseg, int nseg, int heads, int d, bool allow_split, int& grid, Sched& sc) {
   const int nblk = (d + HB - 1) / HB;
   const long long slots = (long long)sm_count() * (nblk == 1 ? Cfg<1>::CTAS : 1);
   const long long units = (long long)((lq + BM - 1) / BM) * heads * b;
   const int t_all = nseg * ((lseg + BN - 1) / BN);
-  int max_p = allow_split ? t_all / DF_MIN_PART_TILES : 1;
-  if (max_p < 1) max_p = 1;
   if (units >= slots) {
     grid = (int)slots;
     sc.a = (int)(units / slots);
     sc.R = (int)(units % slots);
     sc.P = 1;
-    if (sc.R > 0) {
-      long long p = slots / sc.R;
-      if (p > max_p) p = max_p;
-      sc.P = (int)(p < 1 ? 1 : p);
-    }
   } else {
-    long long p = slots / units;
-    if (p > max_p) p = max_p;
+    long long p = allow_split ? slots / units : 1;
+    if (p > t_all / DF_MIN_PART_TILES) p = t_all / DF_MIN_PART_TILES;
     if (p < 1) p = 1;
     sc.a = 0; sc.R = (int)units; sc.P = (int)p;
     grid = (int)(units * p);

@@ -47,10 +47,10 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (2, 2048, 300, 20, 64),        # persistent CTAs: 640 units x 3 tiles, ragged last tile
     (2, 1100, 520, 8, 80),         # persistent CTAs, two head blocks, one CTA per SM: 144 units (< 148) and ragged q
     (2, 2304, 260, 8, 160),        # persistent CTAs, three head blocks: 288 units on 148 CTAs
-    (2, 1024, 1024, 20, 64),       # SDXL 1024^2 level 2: 320 units on 296 CTAs -> 24 left-over units in 4 parts, merged in-kernel
-    (2, 4096, 1024, 10, 64),       # 640 units: two whole units per CTA + 48 left-over units in parts
-    (1, 256, 1024, 20, 64),        # SDXL 1024^2 n=4 level 2: 40 units spread over the idle SMs (every unit is "left over")
-    (1, 200, 2000, 3, 80),         # left-over parts with two head blocks, ragged q and k/v
+    (2, 1024, 1024, 20, 64),       # SDXL 1024^2 level 2: 320 units on 296 CTAs (24 CTAs take a second unit)
+    (2, 4096, 1024, 10, 64),       # 640 units: two whole units per CTA + 48 left-over units
+    (1, 256, 2048, 20, 64),        # 40 units x 16 tiles on 296 slots: 2 K/V parts per unit, merged in-kernel by the last arriver
+    (1, 200, 3000, 3, 80),         # split units with two head blocks, ragged q and k/v
 ])
 def test_attention_single_segment(b, lq, lk, heads, d):
     torch.manual_seed(0)
@@ -68,7 +68,8 @@ def test_attention_tail_split_is_planned():
     from distrifuser_b200 import _lib
     L = _lib.lib()
     assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > 0         # 8 units on 296 slots, 64 K/V tiles
-    assert L.df_attn_workspace_bytes(2, 1024, 1024, 1, 20, 64) > 0       # 320 units: 24 left over
+    assert L.df_attn_workspace_bytes(2, 1024, 1024, 1, 20, 64) == 0      # 320 units fill the 296 slots: left-overs stay whole
+    assert L.df_attn_workspace_bytes(1, 1024, 4096, 1, 10, 64) > 0       # SDXL 1024^2 n=4 level 1: 80 units x 32 tiles -> 3 parts
     assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile, nothing to cut
     assert L.df_attn_workspace_bytes(1, 3600, 3600, 4, 20, 64) == 0      # 580 units: 284 left over on 296 slots -> whole
 

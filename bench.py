@@ -422,7 +422,7 @@ def groupnorm_roofline(gn_shapes, dev, peaks, eager_bytes, eager_ms, eager_launc
     def launch_all():
         st = torch.cuda.current_stream().cuda_stream
         for x, y, g_, b_, scr, (bb, cc, hh, ww) in items:
-            _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), x.data_ptr(), None, y.data_ptr(), g_.data_ptr(), b_.data_ptr(), bb, hh, ww, cc, 32,
+            _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), x.data_ptr(), None, 0, y.data_ptr(), g_.data_ptr(), b_.data_ptr(), bb, hh, ww, cc, 32,
                                           1e-5, 0, 0, 0, 1, 0, 0, 0, 1, scr.data_ptr(), st), "df_groupnorm_fwd")
     side = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(side):

@@ -52,9 +52,9 @@ def lib():
         L.df_slot_wait.argtypes = [DfComm, i32, u32, vp]
         L.df_groupnorm_scratch_bytes.argtypes = [i32, i32, i32, i32, i32]
         L.df_groupnorm_scratch_bytes.restype = C.c_size_t
-        L.df_groupnorm_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
+        L.df_groupnorm_fwd.argtypes = [DfComm, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
                                        u64, u64, u32, vp, vp]
-        L.df_groupnorm_halo_fwd.argtypes = [DfComm, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
+        L.df_groupnorm_halo_fwd.argtypes = [DfComm, vp, vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, f32, i32, i32, i32, i32, i32,
                                             u64, u64, u32, vp, i32, u64, u64, i32, i32, i32, i32, vp]
         L.df_halo_push.argtypes = [DfComm, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, vp]
         L.df_halo_assemble.argtypes = [DfComm, vp, vp, i32, i32, i32, i32, i32, u64, u64, i32, i32, i32, vp]

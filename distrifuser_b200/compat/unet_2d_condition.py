@@ -190,6 +190,7 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
         self.output_scale_factor = 1.0
         self.fused_norm_act = False      # DistriUNetPP turns this on: SiLU runs inside the GroupNorm kernel
+        self.temb_proj = None            # [b, cout] view set by the UNet per call: time_emb_proj(silu(temb)) of ALL blocks in one GEMM
 
     def forward(self, x, temb):
         fused_halo = self.fused_norm_act and hasattr(self.conv1, "halo_plan")    # DistriGroupNorm -> DistriConv2dPP pairs
@@ -200,7 +201,7 @@ class ResnetBlock2D(nn.Module):
             if not self.fused_norm_act:
                 h = self.nonlinearity(h)
             h = self.conv1(h)
-        t = self.time_emb_proj(self.nonlinearity(temb))
+        t = self.temb_proj if self.temb_proj is not None else self.time_emb_proj(self.nonlinearity(temb))
         if fused_halo and self.conv2.halo_plan(h) is not None:
             h = self.conv2.forward_padded(self.norm2(h, addend=t, pad_for=self.conv2))
         else:
@@ -351,6 +352,35 @@ class UNet2DConditionModel(nn.Module):
     def dtype(self):
         return self.conv_in.weight.dtype
 
+    def _resnets(self):
+        return [m for m in self.modules() if isinstance(m, ResnetBlock2D)]
+
+    def _batched_temb(self, emb):
+        """time_emb_proj(silu(emb)) of every ResnetBlock2D as ONE GEMM + one SiLU per UNet call instead of 17 tiny pairs (the
+        activation function and the embedding are the same for all blocks); the concatenated weight follows the blocks' weights
+        (version counters).  Sets blk.temb_proj views; a no-op on CPU / non-fp16 (reference path of the tests)."""
+        blocks = self._resnets()
+        if not (emb.is_cuda and emb.dtype == torch.float16) or not blocks:
+            for blk in blocks:
+                blk.temb_proj = None
+            return
+        key = tuple((blk.time_emb_proj.weight._version, blk.time_emb_proj.weight.data_ptr(), blk.time_emb_proj.bias._version)
+                    for blk in blocks)
+        cache = getattr(self, "_temb_cache", None)
+        if cache is None or cache[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("time-embedding weights changed since the last eager call; run one eager UNet call before capture")
+            with torch.no_grad():
+                w = torch.cat([blk.time_emb_proj.weight.detach() for blk in blocks], 0).contiguous()
+                b = torch.cat([blk.time_emb_proj.bias.detach() for blk in blocks], 0).contiguous()
+            self._temb_cache = cache = (key, w, b)
+        allp = F.linear(F.silu(emb), cache[1], cache[2])
+        o = 0
+        for blk in blocks:
+            n = blk.time_emb_proj.out_features
+            blk.temb_proj = allp[:, o:o + n]
+            o += n
+
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None, attention_mask=None,
                 cross_attention_kwargs=None, added_cond_kwargs=None, down_block_additional_residuals=None,
                 mid_block_additional_residual=None, down_intrablock_additional_residuals=None,
@@ -367,6 +397,7 @@ class UNet2DConditionModel(nn.Module):
             text, ids = added_cond_kwargs["text_embeds"], added_cond_kwargs["time_ids"]
             tid = sinusoid(ids.flatten(), c.addition_time_embed_dim).reshape(text.shape[0], -1)
             emb = emb + self.add_embedding(torch.cat([text, tid.to(text.dtype)], dim=-1).to(emb.dtype))
+        self._batched_temb(emb)
         x = self.conv_in(sample)
         skips = [x]
         for blk in self.down_blocks:

@@ -83,7 +83,7 @@ __device__ void gn_publish_async(const GnExchange& e, const float2* mine);
 // STREAM = true: loads bypass L1 (two-kernel path: the data is touched once); false: default caching, so that the apply pass
 // of the fused kernel finds this CTA's pixels in L1 / L2.
 template <bool STREAM>
-__device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, const __half* __restrict__ addend,
+__device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                               float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
                                               int ppc, const GnExchange& ex, float2* ch, bool defer_publish = false) {
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
@@ -95,7 +95,7 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
     float s[8], ss[8], ad[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] = ss[j] = ad[j] = 0.f;
-    if (addend) unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);   // per-(sample, channel) bias, e.g. the time embedding
+    if (addend) unpack8(ld_v4(addend + (size_t)b * addend_pitch + (size_t)v * 8), ad);   // per-(sample, channel) bias, e.g. the time embedding
     int p = p0 + pl;
     constexpr int U = 8;                          // loads in flight per thread (one DRAM latency round per 8 pixels)
     for (; p + (U - 1) * lanes < p1; p += U * lanes) {
@@ -157,11 +157,11 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
   return true;
 }
 
-__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+__global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                                        float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
                                                        int ppc, GnExchange ex) {
   extern __shared__ float2 ch[];  // [lanes][C] per-channel (sum, sum of squares); reused as float2 mine[bG] by the last CTA
-  gn_stats_body<true>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch);
+  gn_stats_body<true>(x, addend, addend_pitch, partial, hw, C, G, V, lanes, ppc, ex, ch);
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
@@ -259,7 +259,7 @@ __device__ void gn_publish_async(const GnExchange& e, const float2* mine) {
 }
 
 template <bool STREAM>
-__device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, const __half* __restrict__ addend,
+__device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                               __half* __restrict__ y, const __half* __restrict__ gamma,
                                               const __half* __restrict__ beta,
                                               const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
@@ -284,7 +284,7 @@ __device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, cons
     }
     if (addend) {                     // y = ((x + a) - mean) * rstd * gamma + beta  ==  x * sc + (sh + a * sc)
       float ad[8];
-      unpack8(ld_v4(addend + (size_t)b * C + (size_t)v * 8), ad);
+      unpack8(ld_v4(addend + (size_t)b * addend_pitch + (size_t)v * 8), ad);
 #pragma unroll
       for (int j = 0; j < 8; ++j) sh[j] = fmaf(ad[j], sc[j], sh[j]);
     }
@@ -371,12 +371,12 @@ __device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, cons
   }
 }
 
-__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+__global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                                        __half* __restrict__ y, const __half* __restrict__ gamma,
                                                        const __half* __restrict__ beta,
                                                        const float2* __restrict__ coef, int hw, int C, int G, int V, int lanes,
                                                        int ppc, int silu, GnHalo halo) {
-  gn_apply_body<true>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
+  gn_apply_body<true>(x, addend, addend_pitch, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
 }
 
 // ONE launch: statistics -> grid-wide hand-over -> normalise.  Every CTA of the grid is resident at once (the host caps the
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
 // that the last CTA bumps after it has reduced / exchanged the statistics and written coef[]; then each CTA normalises the
 // pixels it has just read (L1 / L2 hits: one HBM read and one write per element instead of two reads and one write, and one
 // launch instead of two -- the level-2 GroupNorms of SDXL are launch-bound).
-__global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ addend,
+__global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                                           __half* __restrict__ y, const __half* __restrict__ gamma,
                                                           const __half* __restrict__ beta, float2* __restrict__ partial,
                                                           const float2* __restrict__ coef, int hw, int C, int G, int V,
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
   pdl_wait();
   if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
   __syncthreads();
-  const bool last = gn_stats_body<false>(x, addend, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
+  const bool last = gn_stats_body<false>(x, addend, addend_pitch, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
   if (last) {
     __threadfence();                                     // coef[] (written by this CTA's threads) before the generation bump
     __syncthreads();
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
     }
     __syncthreads();
   }
-  gn_apply_body<false>(x, addend, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
+  gn_apply_body<false>(x, addend, addend_pitch, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
 }
 
 }  // namespace
@@ -422,13 +422,15 @@ extern "C" size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, in
 }
 
 namespace {
-int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
+int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, int64_t addend_pitch, void* y, const void* gamma,
                    const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
                    int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                    uint32_t group_mask, void* scratch, void* stream, GnHalo halo) {
   DF_REQUIRE(C % 8 == 0 && C % groups == 0 && C / 8 <= 512, "df_groupnorm_fwd: unsupported channel count %d", C);
-  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)addend % 16) == 0,
-             "df_groupnorm_fwd: x / y / addend must be 16-byte aligned");
+  DF_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && ((uintptr_t)addend % 16) == 0 && addend_pitch % 8 == 0,
+             "df_groupnorm_fwd: x / y / addend must be 16-byte aligned (addend pitch a multiple of 8 elements)");
+  if (addend == nullptr) addend_pitch = 0;
+  else if (addend_pitch == 0) addend_pitch = C;
   DF_REQUIRE(mode >= 0 && mode <= 3, "df_groupnorm_fwd: bad mode %d", mode);
   DF_REQUIRE(b * groups <= 512 && groups <= 128, "df_groupnorm_fwd: b*groups = %d exceeds the exchange buffer", b * groups);
   DF_REQUIRE(mode == 0 || (slot_bytes >= (uint64_t)b * groups * 8 && (group_mask >> comm.rank & 1)),
@@ -462,15 +464,15 @@ int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, void* y, c
   }
   if (p.nchunk * b <= fused_capacity && smem <= 32 * 1024) {
     unsigned int* gen = ticket + 1;
-    DF_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend,
+    DF_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend, addend_pitch,
                              (__half*)y, (const __half*)gamma, (const __half*)beta, partial, (const float2*)coef, hw, C, groups, p.V,
                              p.lanes, p.ppc, fuse_silu, ex, gen, halo));
     return 0;
   }
-  gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, partial, hw, C, groups,
+  gn_stats_kernel<<<dim3(p.nchunk, b), p.threads, smem, st>>>((const __half*)x, (const __half*)addend, addend_pitch, partial, hw, C, groups,
                                                              p.V, p.lanes, p.ppc, ex);
   DF_CHECK_LAUNCH();
-  gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (const __half*)addend, (__half*)y,
+  gn_apply_kernel<<<dim3(p.nchunk, b), p.threads, 0, st>>>((const __half*)x, (const __half*)addend, addend_pitch, (__half*)y,
                                                            (const __half*)gamma, (const __half*)beta, coef, hw, C, groups, p.V,
                                                            p.lanes, p.ppc, fuse_silu, halo);
   DF_CHECK_LAUNCH();
@@ -478,17 +480,17 @@ int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, void* y, c
 }
 }  // namespace
 
-extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma,
+extern "C" int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, int64_t addend_pitch, void* y, const void* gamma,
                                 const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
                                 int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                                 uint32_t group_mask, void* scratch, void* stream) {
   GnHalo halo;
   memset(&halo, 0, sizeof(halo));
-  return groupnorm_impl(comm, x, addend, y, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu, idx,
+  return groupnorm_impl(comm, x, addend, addend_pitch, y, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu, idx,
                         tensor_off, slot_bytes, group_mask, scratch, stream, halo);
 }
 
-extern "C" int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, void* y_padded, const void* gamma,
+extern "C" int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, int64_t addend_pitch, void* y_padded, const void* gamma,
                                      const void* beta, int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
                                      int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                                      uint32_t group_mask, void* scratch, int halo_idx, uint64_t halo_off,
@@ -499,6 +501,6 @@ extern "C" int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* 
   memset(&halo, 0, sizeof(halo));
   halo.enabled = 1; halo.h = h; halo.w = w; halo.up = up_rank; halo.down = down_rank; halo.push = push; halo.wait_flags = wait_flags;
   halo.idx = halo_idx; halo.off = halo_off; halo.slot_bytes = halo_slot_bytes; halo.c = comm;
-  return groupnorm_impl(comm, x, addend, y_padded, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu,
+  return groupnorm_impl(comm, x, addend, addend_pitch, y_padded, gamma, beta, b, h, w, C, groups, eps, mode, bessel, neg_var_fallback, fuse_silu,
                         idx, tensor_off, slot_bytes, group_mask, scratch, stream, halo);
 }

@@ -76,17 +76,21 @@ class DistriGroupNorm(BaseModule):
         if prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+        apitch = 0
         if addend is not None:
-            addend = addend.reshape(b, c).contiguous()
+            addend = addend.reshape(b, c)
+            if addend.stride(1) != 1 or addend.stride(0) % 8 != 0 or addend.data_ptr() % 16 != 0:
+                addend = addend.contiguous()
+            apitch = addend.stride(0)                 # a column slice of the batched time-embedding projection: no copy
             assert addend.dtype == x.dtype
         st = torch.cuda.current_stream().cuda_stream
         if halo is None:
-            _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
+            _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, apitch, y.data_ptr(), gamma, beta, b, h, w, c, G, float(module.eps),
                                           mode, bessel, neg_fb, int(self.fuse_silu), self.idx or 0, off, sb, mask,
                                           self._scratch.data_ptr(), st), "df_groupnorm_fwd")
         else:
             h_idx, h_off, h_sb, up, down, push = halo
-            _lib.check(L.df_groupnorm_halo_fwd(cm.group, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), gamma,
+            _lib.check(L.df_groupnorm_halo_fwd(cm.group, x.data_ptr(), addend.data_ptr() if addend is not None else None, apitch, y.data_ptr(), gamma,
                                                beta, b, h, w, c, G, float(module.eps), mode, bessel, neg_fb, int(self.fuse_silu),
                                                self.idx or 0, off, sb, mask, self._scratch.data_ptr(), h_idx, h_off, h_sb, up, down,
                                                int(push), 1, st), "df_groupnorm_halo_fwd")

@@ -93,10 +93,10 @@ int df_slot_wait(df_comm_t comm, int idx, uint32_t src_mask, void* stream);
  *      group_mask selects the patch-group members (bit i = group rank i); stats slots hold 2*b*G fp32
  *      (mean, mean of squares).  `scratch` >= df_groupnorm_scratch_bytes(). ---------------------------- */
 size_t df_groupnorm_scratch_bytes(int b, int groups, int h, int w, int C);
-/* `addend` (nullable): [b, C] fp16 added to every pixel before the statistics and the normalisation, i.e. the
+/* `addend` (nullable): [b, C] fp16 (row pitch `addend_pitch` elements, 0 = C) added to every pixel before the statistics and the normalisation, i.e. the
  * kernel computes GroupNorm(x + addend[:, :, None, None]) -- ResnetBlock2D's time-embedding add, fused.
  * `scratch` must be zero-filled once when it is allocated (it carries a self-resetting CTA ticket). */
-int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y, const void* gamma, const void* beta,
+int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, int64_t addend_pitch, void* y, const void* gamma, const void* beta,
                      int b, int h, int w, int C, int groups, float eps, int mode, int bessel,
                      int neg_var_fallback, int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes,
                      uint32_t group_mask, void* scratch, void* stream);
@@ -107,7 +107,7 @@ int df_groupnorm_fwd(df_comm_t comm, const void* x, const void* addend, void* y,
  * df_halo_push) and rows 0 / h+1 are filled from the neighbours' slots of the read epoch, zeros at the image border (replaces
  * df_halo_assemble and its copy of the whole activation; distrifuser/modules/pp/conv2d.py:72-93).  comm must be the patch
  * group even when the statistics mode is 0. */
-int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, void* y_padded, const void* gamma, const void* beta,
+int df_groupnorm_halo_fwd(df_comm_t comm, const void* x, const void* addend, int64_t addend_pitch, void* y_padded, const void* gamma, const void* beta,
                           int b, int h, int w, int C, int groups, float eps, int mode, int bessel, int neg_var_fallback,
                           int fuse_silu, int idx, uint64_t tensor_off, uint64_t slot_bytes, uint32_t group_mask, void* scratch,
                           int halo_idx, uint64_t halo_off, uint64_t halo_slot_bytes, int up_rank, int down_rank, int push,

@@ -171,13 +171,13 @@ def _moments(x, G):
     return x5.mean(dim=[2, 3, 4], keepdim=True), (x5 * x5).mean(dim=[2, 3, 4], keepdim=True)
 
 
-def _gn_call(x, G, w, b_, eps, mode, bessel, negfb, silu, comm, idx, off, sb, mask, addend=None):
+def _gn_call(x, G, w, b_, eps, mode, bessel, negfb, silu, comm, idx, off, sb, mask, addend=None, apitch=0):
     from distrifuser_b200 import _lib
     L = _lib.lib()
     B, Cc, H, W = x.shape
     y = torch.empty_like(x, memory_format=torch.channels_last)
     scratch = torch.zeros(L.df_groupnorm_scratch_bytes(B, G, H, W, Cc), dtype=torch.uint8, device="cuda")
-    _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, y.data_ptr(), w.data_ptr(), b_.data_ptr(), B, H, W, Cc, G, eps, mode,
+    _lib.check(L.df_groupnorm_fwd(comm, x.data_ptr(), addend.data_ptr() if addend is not None else None, apitch, y.data_ptr(), w.data_ptr(), b_.data_ptr(), B, H, W, Cc, G, eps, mode,
                                   bessel, negfb, silu, idx, off, sb, mask, scratch.data_ptr(),
                                   torch.cuda.current_stream().cuda_stream), "df_groupnorm_fwd")
     torch.cuda.synchronize()
@@ -216,6 +216,11 @@ def test_groupnorm_fused_addend_twice():
     for _ in range(2):
         y = _gn_call(x, G, w, b_, 1e-5, 0, 0, 0, 1, _lib.null_comm(), 0, 0, 0, 1, addend=t)
         assert (y.float() - ref).abs().max().item() < 6e-3
+    # the addend as a column slice of a wider matrix (the batched time-embedding projection of all ResnetBlock2D): row pitch
+    wide = torch.randn(B, 3 * Cc, device="cuda").half()
+    wide[:, Cc:2 * Cc] = t
+    y = _gn_call(x, G, w, b_, 1e-5, 0, 0, 0, 1, _lib.null_comm(), 0, 0, 0, 1, addend=wide[:, Cc:2 * Cc], apitch=3 * Cc)
+    assert (y.float() - ref).abs().max().item() < 6e-3
 
 
 @pytest.mark.parametrize("mode_name", ["sync", "corrected_async_gn", "stale_gn"])
@@ -339,7 +344,7 @@ def test_groupnorm_fused_halo(up, down, addend):
     scratch = torch.zeros(L.df_groupnorm_scratch_bytes(b, G, h, w, c), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(2):      # twice: the normalise-pass ticket resets itself
-        _lib.check(L.df_groupnorm_halo_fwd(arena.comm, x.data_ptr(), t.data_ptr() if addend else None, yp.data_ptr(), gw.data_ptr(),
+        _lib.check(L.df_groupnorm_halo_fwd(arena.comm, x.data_ptr(), t.data_ptr() if addend else None, 0, yp.data_ptr(), gw.data_ptr(),
                                            gb.data_ptr(), b, h, w, c, G, 1e-5, 0, 0, 0, 1, 0, 0, 0, 1, scratch.data_ptr(), 1,
                                            arena.tensor_off[1], arena.slot_bytes[1], up, down, 1, 1, st), "df_groupnorm_halo_fwd")
     torch.cuda.synchronize()

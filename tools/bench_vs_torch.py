@@ -69,7 +69,7 @@ for name, (Cc, hh, ww) in {"C=320 128x128": (320, 128, 128), "C=640 64x64": (640
     st = torch.cuda.current_stream().cuda_stream
 
     def ours():
-        _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), xcl.data_ptr(), None, y.data_ptr(), w.data_ptr(), bb.data_ptr(), b, hh, ww, Cc,
+        _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), xcl.data_ptr(), None, 0, y.data_ptr(), w.data_ptr(), bb.data_ptr(), b, hh, ww, Cc,
                                       G, 1e-5, 0, 1, 0, 1, 0, 0, 0, 1, scratch.data_ptr(), st), "gn")
 
     def reference_eager():        # groupnorm.py:37-41,58-72 (local statistics) followed by the block's SiLU

@@ -51,7 +51,7 @@ if "gn" in which:
         bb = torch.randn(Cc, device="cuda", dtype=torch.float16)
         y = torch.empty_like(x)
         scratch = torch.zeros(L.df_groupnorm_scratch_bytes(b, G, hh, ww, Cc), dtype=torch.uint8, device="cuda")
-        profiled(lambda: _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), x.data_ptr(), None, y.data_ptr(), w.data_ptr(), bb.data_ptr(), b,
+        profiled(lambda: _lib.check(L.df_groupnorm_fwd(_lib.null_comm(), x.data_ptr(), None, 0, y.data_ptr(), w.data_ptr(), bb.data_ptr(), b,
                                                        hh, ww, Cc, G, 1e-5, 0, 1, 0, 1, 0, 0, 0, 1, scratch.data_ptr(), st), "gn"))
 if "geglu" in which:
     for (rows, C4) in [(2 * 4096, 4 * 640), (2 * 1024, 4 * 1280)]:

@@ -334,7 +334,7 @@ class PatchParallelismCommManager:
         if num_ctas is None:
             # synchronous steps wait for the data right away: use the whole NVLink; asynchronous publication hides under the
             # attention that follows and should take few SM slots
-            num_ctas = int(os.environ.get("DF_PUB_CTAS", "24")) if async_stream else 296
+            num_ctas = int(os.environ.get("DF_PUB_CTAS", "64")) if async_stream else 296
         main = torch.cuda.current_stream()
         if async_stream:
             self.comm_stream.wait_stream(main)      # fork: publication overlaps the compute that follows

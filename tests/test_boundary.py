@@ -33,6 +33,8 @@ def test_library_is_sm100a_tcgen05(libpath):
     assert "sm_100a" in sass or "SM100" in sass.upper()
     for mnemonic in ("UTCHMMA", "LDTM", "STTM", "UTMALDG"):
         assert mnemonic in sass, f"{mnemonic} missing: the attention kernel is not a tcgen05/TMA kernel"
+    assert "UTCHMMA.2CTA" in sass, "the GEMM must issue CTA-pair (cta_group::2) tensor-core instructions"
+    assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync tensor path in the library"
 
 
 def test_error_channel(libpath):

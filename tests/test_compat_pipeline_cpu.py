@@ -82,3 +82,34 @@ def test_launch_summarizer_families(tmp_path):
     assert m.family("<unnamed>::add_layernorm_kernel<5>(...)").startswith("OURS add_layernorm")
     assert m.family("nvjet_hsh_192x256_64x5_2x1_2cta_v_bz_bias_TNT") == "library GEMM (cuBLAS)"
     assert "elementwise" in m.family("void at::vectorized_elementwise_kernel<8, at::CUDAFunctor_add<c10::Half>>")
+    # cuDNN's sm100 convolutions are cutlass3x "... implicit_gemm_fprop ..." kernels: they must not be booked as cuBLAS (round-1 bug)
+    assert m.family("cutlass3x_sm100_tensorop_s256x256x16implicit_gemm_fprop_f16_f16_f32_void_f16_...") == "library conv (cuDNN)"
+    assert m.family("void <unnamed>::linear_kernel<1, 256>(CUtensorMap_st, CUtensorMap_st, <unnamed>::LinearArgs)").startswith("OURS tcgen05 GEMM")
+    assert m.family("<unnamed>::gn_fused_kernel(const __half *, ...)").startswith("OURS gn_fused")
+
+
+def test_geglu_interleave_layout():
+    """Rows of the fused GEGLU weight: [hidden block t | gate block t] per tile (ops.geglu_interleave), blocks of 80 / 128."""
+    import torch
+    from distrifuser_b200 import ops
+    for block, D in ((128, 512), (80, 320)):
+        w = torch.arange(2 * D * 3, dtype=torch.float32).reshape(2 * D, 3)
+        b = torch.arange(2 * D, dtype=torch.float32)
+        wi, bi = ops.geglu_interleave(w, b, block)
+        for t in range(D // block):
+            assert torch.equal(wi[2 * t * block:(2 * t + 1) * block], w[t * block:(t + 1) * block])                 # hidden
+            assert torch.equal(wi[(2 * t + 1) * block:(2 * t + 2) * block], w[D + t * block:D + (t + 1) * block])   # gate
+            assert torch.equal(bi[(2 * t + 1) * block:(2 * t + 2) * block], b[D + t * block:D + (t + 1) * block])
+
+
+def test_batched_time_embedding_is_noop_on_cpu():
+    """compat UNet: the one-GEMM time-embedding projection is a CUDA fp16 fast path; on CPU every block projects itself."""
+    import torch
+    from distrifuser_b200.compat.unet_2d_condition import SD15, UNet2DConditionModel
+    cfg = dict(SD15, block_out_channels=(32, 64), down_block_types=("DownBlock2D", "DownBlock2D"), up_block_types=("UpBlock2D", "UpBlock2D"),
+               attention_head_dim=(2, 2), transformer_layers_per_block=(1, 1), norm_num_groups=8, cross_attention_dim=16)
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(**cfg).eval()
+    assert len(unet._resnets()) == 2 * 2 + 2 + 2 * 3            # down (2 x 2) + mid (2) + up (2 x 3)
+    unet._batched_temb(torch.randn(1, 128))                     # fp32 CPU embedding: nothing is batched
+    assert all(blk.temb_proj is None for blk in unet._resnets())

@@ -647,7 +647,7 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
       DF_CHECK_CUDA(cudaFuncSetAttribute(fmha_fwd_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)); \
       attr_set = true;                                                                                                       \
     }                                                                                                                        \
-    DF_CHECK_CUDA(launch_pdl(fmha_fwd_kernel<NB>, grid, dim3(NTHREADS), smem_bytes, (cudaStream_t)stream, tq, tkv,           \
+    DF_CHECK_CUDA(launch_pdl(PDL_ATTN, fmha_fwd_kernel<NB>, grid, dim3(NTHREADS), smem_bytes, (cudaStream_t)stream, tq, tkv,           \
                              (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg,        \
                              own_seg, idx, wait_flags, sc, sched, part_o, part_ml, part_cnt));                               \
   }

@@ -17,13 +17,14 @@ void set_error(const char* fmt, ...) {
 }
 }  // namespace df
 
-bool df::pdl_enabled() {
+unsigned df::pdl_mask() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("DF_PDL");
-    v = (e && e[0] == '1') ? 1 : 0;      // opt-in: measured neutral on a 1-GPU 1024^2 step (profiles/r2_pdl_ab.txt)
+    const char* e = getenv("DF_PDL");          // opt-in: measured neutral on a 1-GPU 1024^2 step (profiles/r2_pdl_ab.txt)
+    v = e ? atoi(e) : 0;
+    if (v < 0) v = 0;
   }
-  return v != 0;
+  return (unsigned)v;
 }
 
 using namespace df;

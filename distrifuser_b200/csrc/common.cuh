@@ -90,13 +90,15 @@ __device__ __forceinline__ void st_v4(void* p, const int4& v) {
 // A denoise step is a chain of ~1 400 short kernels; with the launch attribute below a kernel of this library may be scheduled
 // while its predecessor in the stream is still draining, run its prologue (TMEM / barrier set-up, tensor-map prefetch, index
 // arithmetic) and then block in pdl_wait() until the predecessor has completed and flushed its writes.  No global memory is
-// read or written before pdl_wait().  Opt-in with DF_PDL=1 (without the attribute the device-side wait is a no-op).
-bool pdl_enabled();
+// read or written before pdl_wait().  Opt-in per kernel family with the DF_PDL bit mask (without the attribute the device-side wait
+// is a no-op).
+unsigned pdl_mask();   // DF_PDL bit mask: 1 attention, 2 add+LayerNorm / GEGLU, 4 GroupNorm, 8 GEMM (0 = off, default)
+enum { PDL_ATTN = 1, PDL_ELEM = 2, PDL_GN = 4, PDL_GEMM = 8 };
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+inline cudaError_t launch_pdl(unsigned family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -104,7 +106,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_mask() & family) ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);

@@ -53,7 +53,7 @@ extern "C" int df_geglu(const void* in, void* out, int64_t rows, int cols, int64
   const int64_t total = rows * (cols / 8);
   int64_t g = (total + 255) / 256;
   if (g > 148 * 16) g = 148 * 16;
-  DF_CHECK_CUDA(launch_pdl(geglu_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, (const __half*)in, (__half*)out, rows,
+  DF_CHECK_CUDA(launch_pdl(PDL_ELEM, geglu_kernel, dim3((unsigned)g), dim3(256), 0, (cudaStream_t)stream, (const __half*)in, (__half*)out, rows,
                            cols / 8, in_pitch, out_pitch, cols));
   return 0;
 }
@@ -152,7 +152,7 @@ extern "C" int df_add_layernorm(const void* x, const void* r, void* s_out, void*
   const unsigned grid = (unsigned)((rows + warps - 1) / warps);
   cudaStream_t st = (cudaStream_t)stream;
   const int nvec = C / 8;
-#define DF_LN(MV) DF_CHECK_CUDA(launch_pdl(add_layernorm_kernel<MV>, dim3(grid), dim3(warps * 32), 0, st, (const __half*)x, (const __half*)r, \
+#define DF_LN(MV) DF_CHECK_CUDA(launch_pdl(PDL_ELEM, add_layernorm_kernel<MV>, dim3(grid), dim3(warps * 32), 0, st, (const __half*)x, (const __half*)r, \
       (__half*)s_out, (__half*)y, (const __half*)gamma, (const __half*)beta, rows, C, eps))
   if (nvec <= 32 * 2) DF_LN(2); else if (nvec <= 32 * 3) DF_LN(3); else if (nvec <= 32 * 5) DF_LN(5); else DF_LN(8);
 #undef DF_LN

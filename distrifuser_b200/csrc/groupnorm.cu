@@ -14,6 +14,14 @@ using namespace df;
 
 namespace {
 
+#ifdef DF_GN_TRACE
+// %globaltimer stamps of one launch for kernel tuning (tools/trace_gn.py); compiled out by default
+__device__ unsigned long long df_gn_trace[16];
+#define GN_TR(slot, cond) do { if (cond) df_gn_trace[slot] = globaltimer_ns(); } while (0)
+#else
+#define GN_TR(slot, cond) do {} while (0)
+#endif
+
 struct GnPlan {
   int V;        // 16-byte channel vectors per pixel (C/8)
   int lanes;    // pixels processed concurrently by one CTA
@@ -119,6 +127,7 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) ch[(size_t)pl * C + v * 8 + j] = make_float2(s[j], ss[j]);
   }
+  GN_TR(1, blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
   __syncthreads();
   // fold channels x pixel-lanes into the G groups in a FIXED order (no atomics: results are bit-reproducible run to run)
   __shared__ float2 fold[256];
@@ -151,9 +160,12 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
     if (is_last) *ex.ticket = 0;
   }
   __syncthreads();
+  GN_TR(2, blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
   if (!is_last) return false;
   __threadfence();
+  GN_TR(3, tid == 0);
   gn_exchange(ex, partial, G, nchunk, ch, defer_publish);
+  GN_TR(4, tid == 0);
   return true;
 }
 
@@ -393,6 +405,7 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
   extern __shared__ float2 ch[];
   __shared__ unsigned int my_gen;
   pdl_wait();
+  GN_TR(0, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
   __syncthreads();
   const bool last = gn_stats_body<false>(x, addend, addend_pitch, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
@@ -411,8 +424,21 @@ __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restri
     }
     __syncthreads();
   }
+  GN_TR(5, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   gn_apply_body<false>(x, addend, addend_pitch, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
+  GN_TR(6, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  GN_TR(7, last && threadIdx.x == 0);
 }
+
+#ifdef DF_GN_TRACE
+}  // namespace
+extern "C" int df_debug_gn_trace(unsigned long long* out_host /* 16 */) {
+  DF_CHECK_CUDA(cudaDeviceSynchronize());
+  DF_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, df_gn_trace, sizeof(unsigned long long) * 16));
+  return 0;
+}
+namespace {
+#endif
 
 }  // namespace
 
@@ -464,7 +490,7 @@ int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, int64_t ad
   }
   if (p.nchunk * b <= fused_capacity && smem <= 32 * 1024) {
     unsigned int* gen = ticket + 1;
-    DF_CHECK_CUDA(launch_pdl(gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend, addend_pitch,
+    DF_CHECK_CUDA(launch_pdl(PDL_GN, gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend, addend_pitch,
                              (__half*)y, (const __half*)gamma, (const __half*)beta, partial, (const float2*)coef, hw, C, groups, p.V,
                              p.lanes, p.ppc, fuse_silu, ex, gen, halo));
     return 0;

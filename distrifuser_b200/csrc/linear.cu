@@ -333,7 +333,7 @@ int launch_linear(const CUtensorMap& ta, const CUtensorMap& tw, const LinearArgs
     DF_CHECK_CUDA(cudaFuncSetAttribute(linear_kernel<EPI, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemT<BN>)));
     attr_set = true;
   }
-  DF_CHECK_CUDA(launch_pdl(linear_kernel<EPI, BN>, dim3(ctas), dim3(NTHREADS), sizeof(SmemT<BN>), st, ta, tw, args));   // cluster of 2: __cluster_dims__
+  DF_CHECK_CUDA(launch_pdl(PDL_GEMM, linear_kernel<EPI, BN>, dim3(ctas), dim3(NTHREADS), sizeof(SmemT<BN>), st, ta, tw, args));   // cluster of 2: __cluster_dims__
   return 0;
 }
 

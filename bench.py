@@ -104,6 +104,42 @@ def load_peaks() -> dict:
 
 
 # ------------------------------------------------------------------------------------------------ reference arm / cpu baseline
+def usable_cpus() -> int:
+    """CPUs this process may really use: the smaller of os.cpu_count(), the affinity mask and the cgroup CPU quota."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def pick_cpu_threads(torch) -> int:
+    """Thread count for the CPU reference legs: the fastest of {usable CPUs, 1/2, 1/4} on a 1536^3 fp32 matmul probe (a shared
+    128-thread host ran the full-UNet step 25x slower with all threads than round 1's 64-thread hosts; oversubscribed OpenMP teams
+    spin on every one of the ~2 000 ops of a step)."""
+    n = usable_cpus()
+    a = torch.randn(1536, 1536)
+    best, best_t = n, None
+    for cand in sorted({n, max(1, n // 2), max(1, n // 4)}, reverse=True):
+        torch.set_num_threads(cand)
+        a @ a
+        dt = float("inf")
+        for _ in range(4):
+            t0 = time.perf_counter()
+            a @ a
+            dt = min(dt, time.perf_counter() - t0)
+        if best_t is None or dt < 0.9 * best_t:
+            best, best_t = cand, dt
+    return best
+
+
 FLOPS_STEP = {512: 3.18e12, 1024: 13.52e12, 2048: 71.82e12, 3840: 464.92e12}   # SDXL, per CFG-pair denoise step (SURVEY Appendix B)
 
 
@@ -118,7 +154,7 @@ def cpu_reference_samples(model: str, resolution: int, want_timed: int, want_war
     import torch
     from oracle import pp_modules, workloads
     t_begin = time.perf_counter()
-    threads = int(os.environ.get("DF_CPU_THREADS", "0")) or (os.cpu_count() or 1)
+    threads = int(os.environ.get("DF_CPU_THREADS", "0")) or pick_cpu_threads(torch)
     torch.set_num_threads(threads)                      # torchrun exports OMP_NUM_THREADS=1: do not inherit it silently
     family = "sdxl" if model == "sdxl" else "sd15"
     target_resolution = resolution

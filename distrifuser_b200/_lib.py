@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdistrifuser_b200.so")
+LIB_PATH = os.environ.get("DF_LIB_PATH") or os.path.join(HERE, "libdistrifuser_b200.so")   # DF_LIB_PATH: a prebuilt variant (kernel experiments)
 
 NBANKS = 3
 MAX_WORLD = 8

@@ -23,14 +23,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str | None = None, csrc: str | None = None) -> str:
+    """`out` / `csrc`: build a variant (DF_NVCC_FLAGS, another source tree) next to the shipped library for A/B runs (DF_LIB_PATH)."""
+    if out or csrc:
+        force = True
     if not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libdistrifuser_b200.so")
     extra = os.environ.get("DF_NVCC_FLAGS", "").split()          # e.g. -DDF_EMU_PAIRS_OF_8=0 for kernel experiments
-    cmd = [nvcc, *FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES]]
+    cmd = [nvcc, *FLAGS, *extra, "-I", os.path.join(HERE, "..", "include"), "-o", out or LIB, *[os.path.join(csrc or CSRC, s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -38,7 +41,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

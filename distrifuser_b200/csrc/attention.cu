@@ -7,15 +7,16 @@
 //     F.scaled_dot_product_attention -> S = Q K^T and O += P V as tcgen05.mma tiles, accumulators in TMEM
 // and the SDPA of DistriCrossAttentionPP.forward (attn.py:79-87) with nseg = 1, lseg = 77.
 //
-// CTA = one 128-row Q tile of one (batch, head).  320 threads, TWO CTAs per SM (256 TMEM columns, ~97 KB smem each):
-//   warps 0-7  softmax: every S row is shared by two threads (warp q handles columns [0,64) of rows 32q.., warp q+4 the
-//              columns [64,128) of the same rows), so 4 softmax warps live on every SM sub-partition (2 CTAs x 2) and hide
-//              each other's fixed-latency stalls -- with one thread per row the kernel sat at 54 % issue utilisation with
-//              "wait" as the top stall (profiles/r1_fmha_v1c_3840.txt).  tcgen05.ld S, partial max exchanged through smem,
-//              exp2 (packed FFMA2/FADD2, part polynomial), P back to TMEM as fp16, lazy O correction, epilogue O/l -> HBM
-//   warp 8     TMA producer: Q once, then K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
+// Persistent CTAs (320 threads, TWO per SM at d <= 64: 256 TMEM columns, ~97 KB smem each) walk work units = one 128-row Q
+// tile of one (batch, head):
+//   warps 0-7  softmax: warp w owns 16 rows and all 128 S columns of them in the 16x256b TMEM fragment layout (a row lives in
+//              one quad).  tcgen05.ld S -> exp2 in place (packed FFMA2/FADD2, a quarter of the lanes on a polynomial instead
+//              of MUFU) against a SPECULATIVE exponent reference -- row maxima are only computed for the first tile of a unit
+//              and for the rare tile whose row sums show the reference was too small -- then P -> fp16 -> TMEM, lazy O
+//              correction, epilogue O / l -> HBM (or fp32 partials merged by the last part of a split unit)
+//   warp 8     TMA producer: Q per unit, then K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
 //   warp 9     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
-//              issued as soon as the softmax warps have pulled S_j into registers (s_free), i.e. under their exp work
+//              issued once the softmax warps have released S_j (s_free)
 // TMEM columns: S [0,128) P [128,192) O [192, 192 + 64*NBLK)   (fp32 S/O, packed fp16 P)
 
 #include "tc_ptx.cuh"
@@ -73,9 +74,12 @@ struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
 };
 
-#ifndef DF_EMU_QUARTERS
-#define DF_EMU_QUARTERS 1    // v3: of every 4 column groups, this many take the polynomial exp2 (FMA/ALU pipes) instead of MUFU
+#ifndef DF_OPAQUE_BASES
+#define DF_OPAQUE_BASES 1
 #endif
+#ifndef DF_EMU_GROUPS
+#define DF_EMU_GROUPS 4      // of the 16 column groups of a tile row, this many (evenly spread) take the polynomial exp2 (FMA/ALU
+#endif                       // pipes) instead of MUFU
 
 #ifdef DF_TRACE
 // cycle-level event trace of CTA (0,0,0) for kernel tuning (tools/trace_attn.py); compiled out by default
@@ -267,8 +271,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     // (profiles/r2_attn_sweep_v4.txt) -- and was removed.
     const int quad = warp & 3, hr = warp >> 2;
     const uint32_t lane16 = (uint32_t)(quad * 32 + hr * 16);
-    const uint32_t lane_base = tmem + (lane16 << 16);
+    uint32_t lane_base = tmem + (lane16 << 16);
+    // shared-window address of the barrier block, computed once: left to itself ptxas rebuilds it (S2R SR_CgaCtaId + LEA)
+    // and lane_base (S2R SR_TID + 5 ALU ops) at every use inside the tile loop instead of holding two registers
+    uint32_t bars = smem_u32(&sm.q_full);
+#if DF_OPAQUE_BASES
+    asm volatile("" : "+r"(lane_base), "+r"(bars));
+#endif
+#define DF_BAR(member) (bars + (uint32_t)(offsetof(Smem, member) - offsetof(Smem, q_full)))
     const int c4 = lane & 3, r8 = lane >> 2;
+    constexpr bool HOLD_S = Cfg<NBLK>::CTAS == 2;                  // see "speculative exponent reference" below
     uint32_t g = 0, ui = 0;                                        // K/V tiles / work units processed so far by this CTA (barrier phases)
     for (int it = 0; it < n_items; ++it, ++ui) {
     int q0, head, bat, j_begin, T, slot, lo;
@@ -279,60 +291,76 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int j = 0; j < T; ++j, ++t, ++g) {
       if (t == tps) t = 0;
       const int valid = min(BN, lseg - t * BN);
-      mbar_wait(&sm.s_full, g & 1u);
+      mbar_wait(DF_BAR(s_full), g & 1u);
       tc_fence_after();
       if (threadIdx.x == 0) DF_TR(0, g);
-      uint32_t sr[64];
-      tmem_ld_16x256b_x16(lane_base + COL_S, sr);
-      tmem_wait_ld();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.s_free);        // the tensor core may overwrite S with Q K_{j+1}^T now
-      if (threadIdx.x == 0) DF_TR(1, g);
-      if (valid < BN) {                              // ragged last tile of a segment only (warp-uniform branch)
-        asm volatile("" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-#pragma unroll
-          for (int k = 0; k < 2; ++k)
-            if (8 * i + 2 * c4 + k >= valid) { sr[4 * i + k] = 0xff800000u; sr[4 * i + 2 + k] = 0xff800000u; }
-      }
-      float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
-#pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        mA0 = max3(mA0, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
-        mB0 = max3(mB0, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
-        mA1 = max3(mA1, __uint_as_float(sr[4 * i + 4]), __uint_as_float(sr[4 * i + 5]));
-        mB1 = max3(mB1, __uint_as_float(sr[4 * i + 6]), __uint_as_float(sr[4 * i + 7]));
-      }
-      float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
-      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
-      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
-      mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
-      mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-      if (threadIdx.x == 0) DF_TR(2, g);
-      // lazy rescale: keep the old reference while the max moved by < 2^8 (P stays < 256, exact in fp32 sums)
-      float alphaA = 1.f, alphaB = 1.f;
+      // SPECULATIVE EXPONENT REFERENCE (HOLD_S, the two-CTAs-per-SM configuration).  Only the first tile of a unit computes the
+      // row maxima before its exponentials.  Every later tile exponentiates against the reference it inherited -- no FMNMX
+      // pass, no quad shuffles, no max -> exp dependency -- and then proves the guess was harmless: P is stored as fp16, so it
+      // is enough that no value reached 2^13, which the row sums the tile needs anyway show (a thread's 32 values of a row sum
+      // to more than 2^13 only if one of them exceeded 2^8; the polynomial lanes, whose exponent insertion wraps for x >= 128,
+      // are covered by the largest integer part they produced).  S_j stays in TMEM until the check has passed, so the rare
+      // failing tile is simply loaded again and redone the classic way (maxima first, O and l rescaled).  The price is that
+      // Q K_{j+1}^T is issued after the exponentials of tile j instead of under them; it still runs under the fp16 packing,
+      // the P store and the other CTA's softmax.
+#ifdef DF_EXPERIMENT_EARLY_RELEASE     // timing experiment only (no redo possible): what holding S costs
+      constexpr bool RELEASE_EARLY = true;
+      bool exact = j == 0;
+#else
+      constexpr bool RELEASE_EARLY = !HOLD_S;
+      bool exact = !HOLD_S || j == 0;
+#endif
       bool moved = false;
-      if ((mA - m_refA) * scale_log2 > 8.f) { alphaA = ex2((m_refA - mA) * scale_log2); m_refA = mA; lA *= alphaA; moved = true; }
-      if ((mB - m_refB) * scale_log2 > 8.f) { alphaB = ex2((m_refB - mB) * scale_log2); m_refB = mB; lB *= alphaB; moved = true; }
-      const float nA = -m_refA * scale_log2, nB = -m_refB * scale_log2;
-      const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
-      uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
-      // two halves of 32 packed P columns each: the first half is stored while the second is still being exponentiated
-      // (keeps 16 instead of 32 P registers live under the 96-register cap of two CTAs per SM)
+      float alphaA = 1.f, alphaB = 1.f, tA, tB;
+      uint32_t sr[64];
+      for (;;) {
+        tmem_ld_16x256b_x16(lane_base + COL_S, sr);
+        tmem_wait_ld();
+        if (RELEASE_EARLY) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(DF_BAR(s_free));      // the tensor core may overwrite S with Q K_{j+1}^T now
+        }
+        if (threadIdx.x == 0) DF_TR(1, g);
+        if (valid < BN) {                              // ragged last tile of a segment only (warp-uniform branch)
+          asm volatile("" ::: "memory");
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t pr[16];
+          for (int i = 0; i < 16; ++i)
 #pragma unroll
-        for (int ii = 0; ii < 8; ++ii) {
-          const int i = hf * 8 + ii;
+            for (int k = 0; k < 2; ++k)
+              if (8 * i + 2 * c4 + k >= valid) { sr[4 * i + k] = 0xff800000u; sr[4 * i + 2 + k] = 0xff800000u; }
+        }
+        if (exact) {
+          float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            mA0 = max3(mA0, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
+            mB0 = max3(mB0, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
+            mA1 = max3(mA1, __uint_as_float(sr[4 * i + 4]), __uint_as_float(sr[4 * i + 5]));
+            mB1 = max3(mB1, __uint_as_float(sr[4 * i + 6]), __uint_as_float(sr[4 * i + 7]));
+          }
+          float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
+          mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+          mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+          mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+          mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+          if (threadIdx.x == 0) DF_TR(2, g);
+          // lazy rescale: keep the old reference while the max moved by < 2^8
+          if ((mA - m_refA) * scale_log2 > 8.f) { alphaA = ex2((m_refA - mA) * scale_log2); m_refA = mA; lA *= alphaA; moved = true; }
+          if ((mB - m_refB) * scale_log2 > 8.f) { alphaB = ex2((m_refB - mB) * scale_log2); m_refB = mB; lB *= alphaB; moved = true; }
+        }
+        const float nA = -m_refA * scale_log2, nB = -m_refB * scale_log2;
+        const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
+        uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
+        float tmax = 0.f;                              // largest (1.5 * 2^23 + integer part) of the polynomial lanes
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {                 // exponentials IN PLACE (fp32): nothing leaves the registers before the check
           const uint64_t xA = fma2(pack2(__uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1])), scale2, nA2);
           const uint64_t xB = fma2(pack2(__uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3])), scale2, nB2);
           float a0, a1, b0, b1;
-          if ((i & 3) < DF_EMU_QUARTERS) {             // this share of the exponentials runs on the FMA / ALU pipes
-            ex2_poly2(xA, a0, a1);
-            ex2_poly2(xB, b0, b1);
+          if ((i * DF_EMU_GROUPS) / 16 != ((i + 1) * DF_EMU_GROUPS) / 16) {             // this share of the exponentials runs on the FMA / ALU pipes
+            ex2_poly2(xA, a0, a1, tmax);
+            ex2_poly2(xB, b0, b1, tmax);
           } else {
             float x0, x1;
             unpack2(xA, x0, x1); a0 = ex2(x0); a1 = ex2(x1);
@@ -340,44 +368,64 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           }
           sA = add2(sA, pack2(a0, a1));
           sB = add2(sB, pack2(b0, b1));
-          pr[2 * ii] = pack_h2(a0, a1);
-          pr[2 * ii + 1] = pack_h2(b0, b1);
+          sr[4 * i] = __float_as_uint(a0); sr[4 * i + 1] = __float_as_uint(a1);
+          sr[4 * i + 2] = __float_as_uint(b0); sr[4 * i + 3] = __float_as_uint(b1);
         }
-        if (hf == 0) {
-          if (threadIdx.x == 0) DF_TR(3, g);
-          if (j > 0) {
-            mbar_wait(&sm.pv_done, (g - 1) & 1u);  // P buffer free, O quiescent
-            tc_fence_after();
-            if (threadIdx.x == 0) DF_TR(4, g);
-            if (__any_sync(0xffffffffu, moved)) {            // rare: rescale this warp's 16 rows of O
+        {
+          float s0, s1;
+          unpack2(sA, s0, s1); tA = s0 + s1;
+          unpack2(sB, s0, s1); tB = s0 + s1;
+        }
+        if (exact) break;
+        const bool over = !(tA <= 8192.f) || !(tB <= 8192.f) || tmax > 12582912.f + 13.f;   // also true for NaN sums
+        if (!__any_sync(0xffffffffu, over)) break;
+        exact = true;                                  // rare: redo this tile with the maxima first
+      }
+      lA += tA;
+      lB += tB;
+      if (!RELEASE_EARLY) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(DF_BAR(s_free));        // the tensor core may overwrite S with Q K_{j+1}^T now
+      }
+      if (threadIdx.x == 0) DF_TR(3, g);
+      // P -> fp16 -> TMEM in two halves of 32 packed columns (16 instead of 32 packed registers live at a time)
 #pragma unroll
-              for (int blk = 0; blk < NBLK; ++blk) {
-                uint32_t o[32];
-                tmem_ld_16x256b_x8(lane_base + COL_O + blk * HB, o);
-                tmem_wait_ld();
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t pr[16];
 #pragma unroll
-                for (int i2 = 0; i2 < 8; ++i2) {
-                  o[4 * i2] = __float_as_uint(__uint_as_float(o[4 * i2]) * alphaA);
-                  o[4 * i2 + 1] = __float_as_uint(__uint_as_float(o[4 * i2 + 1]) * alphaA);
-                  o[4 * i2 + 2] = __float_as_uint(__uint_as_float(o[4 * i2 + 2]) * alphaB);
-                  o[4 * i2 + 3] = __float_as_uint(__uint_as_float(o[4 * i2 + 3]) * alphaB);
-                }
-                tmem_st_16x256b_x8(lane_base + COL_O + blk * HB, o);
+        for (int ii = 0; ii < 8; ++ii) {
+          const int i = hf * 8 + ii;
+          pr[2 * ii] = pack_h2(__uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
+          pr[2 * ii + 1] = pack_h2(__uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
+        }
+        if (hf == 0 && j > 0) {
+          mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);  // P buffer free, O quiescent
+          tc_fence_after();
+          if (threadIdx.x == 0) DF_TR(4, g);
+          if (exact && __any_sync(0xffffffffu, moved)) {     // rare: rescale this warp's 16 rows of O
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+              uint32_t o[32];
+              tmem_ld_16x256b_x8(lane_base + COL_O + blk * HB, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i2 = 0; i2 < 8; ++i2) {
+                o[4 * i2] = __float_as_uint(__uint_as_float(o[4 * i2]) * alphaA);
+                o[4 * i2 + 1] = __float_as_uint(__uint_as_float(o[4 * i2 + 1]) * alphaA);
+                o[4 * i2 + 2] = __float_as_uint(__uint_as_float(o[4 * i2 + 2]) * alphaB);
+                o[4 * i2 + 3] = __float_as_uint(__uint_as_float(o[4 * i2 + 3]) * alphaB);
               }
+              tmem_st_16x256b_x8(lane_base + COL_O + blk * HB, o);
             }
           }
         }
         tmem_st_16x128b_x8(lane_base + COL_P + hf * 32, pr);
       }
-      {
-        float s0, s1;
-        unpack2(sA, s0, s1); lA += s0 + s1;
-        unpack2(sB, s0, s1); lB += s0 + s1;
-      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.p_full);
+      if (lane == 0) mbar_arrive(DF_BAR(p_full));
       if (threadIdx.x == 0) DF_TR(5, g);
     }
     // ---- epilogue: row sums / references -> shared memory (quad reduce), then O / l -> fp16 -> HBM in the 32x32b layout
@@ -394,7 +442,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
     const float l_row = sm.red_sum[ui & 1][row];        // [unit parity]: a fast warp may already be filling the next unit's sums
     const float m_ref = sm.red_ref[ui & 1][row];
-    mbar_wait(&sm.pv_done, (g - 1) & 1u);
+    mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);
     tc_fence_after();
     const bool partial = slot >= 0;
     const int64_t prow = (int64_t)(partial ? slot : 0) * BM + row;          // row of this part's partial in the workspace
@@ -405,7 +453,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tmem_wait_ld();
     tc_fence_before();                                // O is in registers: the next item's first P V may overwrite the accumulator
     __syncwarp();
-    if (lane == 0) mbar_arrive(&sm.o_free);
+    if (lane == 0) mbar_arrive(DF_BAR(o_free));
     bool finish = !partial;                           // this CTA writes the output rows
     float m_all = m_ref, denom = l_row, w_own = 1.f;
     if (partial) {

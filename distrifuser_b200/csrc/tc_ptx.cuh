@@ -16,28 +16,30 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar_addr) {      // by shared-window address (kept in a register by the caller)
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) { mbar_arrive(smem_u32(bar)); }
 #ifndef DF_TRYWAIT_HINT_NS
 #define DF_TRYWAIT_HINT_NS 200000u
 #endif
-__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar_addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // %3: suspend-time hint (ns): sleep in hardware,
       "selp.u32 %0, 1, 0, p;\n\t}"                                        // polling steals issue slots from the softmax warps
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(DF_TRYWAIT_HINT_NS)
+      : "r"(bar_addr), "r"(parity), "r"(DF_TRYWAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) { return mbar_try(smem_u32(bar), parity); }
 // Waits for the phase with the given parity.  try_wait suspends the thread in hardware for up to DF_TRYWAIT_HINT_NS, so the loop
 // costs two instructions per poll.  Fully inline on purpose: an out-of-line slow path (ABI call + printf) inside the softmax
 // loop made ptxas spill around the call site.  A broken pipeline still becomes a CUDA error instead of a hung GPU: after ~10 s
 // of failed polls the thread traps (define DF_MBAR_DEBUG for a printf naming the barrier).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
   uint32_t polls = 0;
   uint64_t t0 = 0;
@@ -48,13 +50,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       else if (now - t0 > 10000000000ull) {
 #ifdef DF_MBAR_DEBUG
         printf("distrifuser_b200: mbarrier timeout (block %d,%d,%d thread %d bar@%u parity %u)\n", blockIdx.x, blockIdx.y, blockIdx.z,
-               threadIdx.x, smem_u32(bar), parity);
+               threadIdx.x, bar, parity);
 #endif
         __trap();
       }
     }
   }
 }
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait(smem_u32(bar), parity); }
 
 __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -260,7 +264,9 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
 // 2^x for a pair, entirely on the FMA/ALU pipes (the MUFU pipe is the bottleneck of d=64 attention): Cody-Waite split
 // x = n + f by adding 1.5*2^23 with round-to-minus-infinity, degree-3 minimax polynomial for 2^f on [0,1) (rel. err < 1e-4,
 // below the fp16 rounding of P), then n is added straight into the exponent field.
-__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
+// `tmax` collects the largest 1.5*2^23 + floor(x) seen: the exponent insertion below is only valid for floor(x) <= 127, and
+// callers that exponentiate against a guessed reference read the overflow off this value.
+__device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1, float& tmax) {
   float x0, x1;
   unpack2(x2, x0, x1);
   x2 = pack2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
@@ -274,13 +280,10 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
   float r0, r1, q0, q1;
   unpack2(r2, r0, r1);
   unpack2(q2, q0, q1);
+  tmax = max3(tmax, r0, r1);
   p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(r0) << 23));
   p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(r1) << 23));
 }
-#ifndef DF_EMU_PAIRS_OF_8
-#define DF_EMU_PAIRS_OF_8 2   // of every 8 element pairs, this many take the polynomial path
-#endif
-
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);

@@ -40,7 +40,7 @@ def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, w
     (1, 256, 256, 8, 160),         # SD1.x head_dim 160 -> three 64-column blocks (level 2/3 shape at 1024^2, n=4)
     (1, 64, 256, 2, 160),          # SD1.x deepest level: fewer q rows than one tile
     (1, 200, 77, 2, 80),           # SD1.x cross-attention
-    (1, 256, 8192, 4, 64),         # tiny grid, long K/V: split-KV (8 CTAs per q-tile) + combine kernel
+    (1, 256, 8192, 4, 64),         # tiny grid, long K/V: 8 K/V parts per unit, merged in-kernel by the last arriver
     (1, 130, 4100, 3, 64),         # split-KV with ragged q and k/v tiles
     (1, 100, 3000, 2, 40),         # split-KV, zero-padded head dim
     (2, 4096, 77, 10, 64),         # persistent CTAs: 640 one-tile work units on 296 resident CTAs (cross-attention at 1024^2 level 1)
@@ -74,15 +74,41 @@ def test_attention_tail_split_is_planned():
     assert L.df_attn_workspace_bytes(1, 3600, 3600, 4, 20, 64) == 0      # 580 units: 284 left over on 296 slots -> whole
 
 
-def test_attention_large_logits_rescale():
-    """Rows whose running max jumps by > 2^8 between tiles exercise the O-correction path."""
+@pytest.mark.parametrize("case", ["late_tiles_x6", "late_tiles_x40", "some_rows", "one_polynomial_column", "one_mufu_column",
+                                  "ragged_then_large", "split_parts"])
+def test_attention_large_logits_rescale(case):
+    """Later K/V tiles whose logits exceed the first tile's by far more than the fp16 head-room of P: the speculative pass (stale
+    exponent reference, no row maxima) must notice and redo the tile with the maxima first, rescaling O and l.  The cases cover
+    every warp redoing, only the warps of some rows redoing, the overflow sitting in a single column that takes the polynomial
+    exp2 (exponent wrap-around at x >= 128) or the MUFU exp2, a ragged tile before the jump, and split K/V parts."""
     torch.manual_seed(1)
     b, lq, lk, heads, d = 1, 128, 512, 1, 64
-    q = torch.randn(b, lq, d, device="cuda", dtype=torch.float16) * 4
-    kv = torch.randn(b, lk, 2 * d, device="cuda", dtype=torch.float16)
-    kv[:, 300:, :d] *= 6          # later tiles carry much larger logits
+    if case == "ragged_then_large":
+        lq, lk = 200, 777
+    if case == "split_parts":
+        lq, lk, heads = 256, 4096, 2          # 4 units on 296 slots: K/V parts merged by the last arriver
+    q = torch.randn(b, lq, heads * d, device="cuda", dtype=torch.float16) * 4
+    kv = torch.randn(b, lk, 2 * heads * d, device="cuda", dtype=torch.float16)
+    C = heads * d
+    if case == "late_tiles_x6":
+        kv[:, 300:, :C] *= 6
+    elif case == "late_tiles_x40":
+        kv[:, 130:, :C] *= 40
+    elif case == "some_rows":
+        q[:, 16:, :] *= 0.1                   # rows 0..15 (one warp's rows) see the jump, the others barely move
+        kv[:, 256:, :C] *= 12
+    elif case == "one_polynomial_column":
+        kv[:, 256 + 3, :C] *= 60              # column 3 of tile 2: group i = 0 -> polynomial lane
+    elif case == "one_mufu_column":
+        kv[:, 256 + 13, :C] *= 60             # column 13 of tile 2: group i = 1 -> MUFU lane
+    elif case == "ragged_then_large":
+        kv[:, 640:, :C] *= 10
+    elif case == "split_parts":
+        kv[:, 1500:, :C] *= 8
+        kv[:, 3000:, :C] *= 3
     out = _attn(q, kv, heads)
-    ref = sdpa_ref(q, kv[..., :d], kv[..., d:], heads)
+    ref = sdpa_ref(q, kv[..., :C], kv[..., C:], heads)
+    assert torch.isfinite(out).all()
     err = (out.float() - ref).abs().max().item()
     assert err < 4e-3, f"max abs err {err}"
 

@@ -84,8 +84,7 @@ struct GnHalo {
   df_comm_t c;
 };
 
-__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine, bool defer_publish);
-__device__ void gn_publish_async(const GnExchange& e, const float2* mine);
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine);
 
 // Statistics pass of one CTA; returns true in the LAST CTA of the grid after it has run the exchange and written coef[].
 // STREAM = true: loads bypass L1 (two-kernel path: the data is touched once); false: default caching, so that the apply pass
@@ -93,7 +92,7 @@ __device__ void gn_publish_async(const GnExchange& e, const float2* mine);
 template <bool STREAM>
 __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                               float2* __restrict__ partial, int hw, int C, int G, int V, int lanes,
-                                              int ppc, const GnExchange& ex, float2* ch, bool defer_publish = false) {
+                                              int ppc, const GnExchange& ex, float2* ch, bool partials_only = false) {
   const int b = blockIdx.y, chunk = blockIdx.x, nchunk = gridDim.x;
   const int tid = threadIdx.x;
   const int v = tid % V, pl = tid / V;
@@ -150,6 +149,7 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
     for (int part = 0; part < parts; ++part) { a += fold[part * G + g].x; q += fold[part * G + g].y; }
     partial[((size_t)b * nchunk + chunk) * G + g] = make_float2(a, q);
   }
+  if (partials_only) return false;                // fused kernel: grid barrier + per-CTA reduction follow (gn_fused_kernel)
   // last CTA of the grid finishes the job: reduce the partials, exchange with the patch group, write (mean, rstd)
   __shared__ bool is_last;
   __threadfence();
@@ -160,12 +160,9 @@ __device__ __forceinline__ bool gn_stats_body(const __half* __restrict__ x, cons
     if (is_last) *ex.ticket = 0;
   }
   __syncthreads();
-  GN_TR(2, blockIdx.x == 0 && blockIdx.y == 0 && tid == 0);
   if (!is_last) return false;
   __threadfence();
-  GN_TR(3, tid == 0);
-  gn_exchange(ex, partial, G, nchunk, ch, defer_publish);
-  GN_TR(4, tid == 0);
+  gn_exchange(ex, partial, G, nchunk, ch);
   return true;
 }
 
@@ -177,7 +174,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(const __half* __restrict_
 }
 
 // mode: 0 local, 1 synchronous exchange, 2 corrected_async_gn, 3 stale_gn   (see include/distrifuser_b200.h)
-__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine, bool defer_publish) {
+__device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* mine) {
   const df_comm_t& c = e.c;
   float2* __restrict__ coef = e.coef;
   const int bG = e.bG, mode = e.mode, neg_fb = e.neg_fb, idx = e.idx;
@@ -250,24 +247,99 @@ __device__ void gn_exchange(const GnExchange& e, const float2* __restrict__ part
     var *= bessel;                                                                              // :65-66
     coef[i] = make_float2(mean, rsqrtf(var + eps));
   }
-  if (mode >= 2 && !defer_publish) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
+  if (mode >= 2) { __syncthreads(); publish(); }   // asynchronous: ship this step's statistics for the next step
 }
 
-// Asynchronous modes: this step's local statistics (still in `mine`, shared memory) go to the peers' slots of the publish epoch
-// for the NEXT step.  Separate from gn_exchange so that the fused kernel can release the normalise pass first: the peer stores,
-// the system-scope fence and the flag stamps (a few microseconds over NVLink) then run beside it instead of in front of it.
-__device__ void gn_publish_async(const GnExchange& e, const float2* mine) {
+// ---- fused kernel: statistics finished by EVERY CTA for its own sample (no serial exchange in one CTA, no coef[] round trip)
+__device__ __forceinline__ float2 ld_cg_f2(const float2* p) {      // L2 load: the partials were written during this launch
+  float2 r;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+  return r;
+}
+// (mean, mean of squares) of the G groups of sample b over the per-CTA partials, in a FIXED order (bit-reproducible):
+// thread (g, r) sums the partials r, r + tpp, ... of group g (a warp reads 32 consecutive groups of one partial row: coalesced),
+// then G threads fold the tpp pieces.  `red` holds G * tpp entries, `mine` G entries.
+__device__ __forceinline__ void gn_reduce_sample(const float2* __restrict__ partial, int b, int G, int nchunk, float inv_ne,
+                                                 float2* red, float2* mine) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tpp = max(1, min(nthr / G, 16));
+  const float2* src = partial + (size_t)b * nchunk * G;
+  for (int e = tid; e < G * tpp; e += nthr) {
+    const int g = e % G, r = e / G;
+    float s0 = 0.f, q0 = 0.f, s1 = 0.f, q1 = 0.f;
+    int k = r;
+    for (; k + tpp < nchunk; k += 2 * tpp) {              // two loads in flight per thread and iteration
+      const float2 u = ld_cg_f2(src + (size_t)k * G + g), w = ld_cg_f2(src + (size_t)(k + tpp) * G + g);
+      s0 += u.x; q0 += u.y; s1 += w.x; q1 += w.y;
+    }
+    if (k < nchunk) { const float2 u = ld_cg_f2(src + (size_t)k * G + g); s0 += u.x; q0 += u.y; }
+    red[r * G + g] = make_float2(s0 + s1, q0 + q1);
+  }
+  __syncthreads();
+  for (int g = tid; g < G; g += nthr) {
+    float s = 0.f, ss = 0.f;
+    for (int r = 0; r < tpp; ++r) { s += red[r * G + g].x; ss += red[r * G + g].y; }
+    mine[g] = make_float2(s * inv_ne, ss * inv_ne);
+  }
+  __syncthreads();
+}
+
+// This rank's statistics of ALL samples go to the patch group's slots of the publish epoch (one CTA of the grid does this:
+// synchronous exchange -> at once, the peers are waiting; asynchronous modes -> for the next step, off the critical path).
+__device__ void gn_publish_all(const GnExchange& e, const float2* __restrict__ partial, int G, int nchunk, float2* red, float2* mine_b) {
   const df_comm_t& c = e.c;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const uint32_t pub = c.clock[0];
-  for (int p = 0; p < c.world; ++p) {
-    if (!(e.group_mask >> p & 1)) continue;
-    float2* dst = (float2*)slot_ptr(c, p, pub, e.tensor_off, e.slot_bytes, c.rank);
-    for (int i = tid; i < e.bG; i += nthr) dst[i] = mine[i];
+  const int nb = e.bG / G;
+  for (int b = 0; b < nb; ++b) {
+    gn_reduce_sample(partial, b, G, nchunk, e.inv_ne, red, mine_b);
+    for (int p = 0; p < c.world; ++p) {
+      if (!(e.group_mask >> p & 1)) continue;
+      float2* dst = (float2*)slot_ptr(c, p, pub, e.tensor_off, e.slot_bytes, c.rank) + (size_t)b * G;
+      for (int g = tid; g < G; g += nthr) dst[g] = mine_b[g];
+    }
+    __syncthreads();
   }
   __threadfence_system();
   __syncthreads();
   if (tid < c.world && (e.group_mask >> tid & 1)) st_release_sys(c.flags[tid] + (size_t)e.idx * c.world + c.rank, pub);
+}
+
+// (mean, rstd) of the G groups of sample b from this rank's statistics `mine` and, in the exchange modes, the patch group's
+// slots of the read epoch (groupnorm.py:40-66; same arithmetic and order as gn_exchange).
+__device__ __forceinline__ void gn_coef_sample(const GnExchange& e, int b, int G, const float2* mine, float2* coef_s) {
+  const df_comm_t& c = e.c;
+  const int tid = threadIdx.x, nthr = blockDim.x, mode = e.mode;
+  uint32_t rd = 0;
+  if (mode != 0) {
+    rd = mode == 1 ? c.clock[0] : c.clock[1];   // a synchronous exchange reads THIS epoch even inside an asynchronous step
+    if (tid < c.world && (e.group_mask >> tid & 1)) spin_until(c.flags[c.rank] + (size_t)e.idx * c.world + tid, rd, c.spin_timeout_ns);
+    __syncthreads();
+  }
+  const int n = __popc(e.group_mask);
+  for (int g = tid; g < G; g += nthr) {
+    const float2 m = mine[g];
+    float mean = m.x, msq = m.y;
+    if (mode != 0) {
+      float sx = 0.f, sy = 0.f;
+      float2 own_stale = make_float2(0.f, 0.f);
+      for (int p = 0; p < c.world; ++p) {
+        if (!(e.group_mask >> p & 1)) continue;
+        const float2 v = ((const float2*)slot_ptr(c, c.rank, rd, e.tensor_off, e.slot_bytes, p))[(size_t)b * G + g];
+        if (p == c.rank) own_stale = v;
+        sx += v.x; sy += v.y;
+      }
+      const float invn = 1.f / (float)n;
+      if (mode == 1) { mean = sx * invn; msq = sy * invn; }
+      else if (mode == 2) { mean = sx * invn + (m.x - own_stale.x); msq = sy * invn + (m.y - own_stale.y); }
+      else { mean = (sx - own_stale.x + m.x) * invn; msq = (sy - own_stale.y + m.y) * invn; }
+    }
+    float var = msq - mean * mean;
+    if (e.neg_fb && var < 0.f) var = m.y - m.x * m.x;
+    var *= e.bessel;
+    coef_s[g] = make_float2(mean, rsqrtf(var + e.eps));
+  }
+  __syncthreads();
 }
 
 template <bool STREAM>
@@ -288,8 +360,8 @@ __device__ __forceinline__ void gn_apply_body(const __half* __restrict__ x, cons
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int ch = v * 8 + j;
-      float2 mr;                       // plain (coherent) load: in the fused kernel coef[] was written during this launch
-      asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(mr.x), "=f"(mr.y) : "l"(coef + b * G + ch / cpg) : "memory");
+      float2 mr;                       // generic load: coef[] is shared memory in the fused kernel, global otherwise
+      asm volatile("ld.v2.f32 {%0, %1}, [%2];" : "=f"(mr.x), "=f"(mr.y) : "l"(coef + b * G + ch / cpg) : "memory");
       float ga = gamma ? __half2float(gamma[ch]) : 1.f, be = beta ? __half2float(beta[ch]) : 0.f;
       sc[j] = mr.y * ga;
       sh[j] = be - mr.x * sc[j];
@@ -391,43 +463,66 @@ __global__ void __launch_bounds__(512) gn_apply_kernel(const __half* __restrict_
   gn_apply_body<true>(x, addend, addend_pitch, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
 }
 
-// ONE launch: statistics -> grid-wide hand-over -> normalise.  Every CTA of the grid is resident at once (the host caps the
-// grid at the occupancy of this kernel), so the CTAs that finished their partial moments may spin on the generation word
-// that the last CTA bumps after it has reduced / exchanged the statistics and written coef[]; then each CTA normalises the
-// pixels it has just read (L1 / L2 hits: one HBM read and one write per element instead of two reads and one write, and one
-// launch instead of two -- the level-2 GroupNorms of SDXL are launch-bound).
+// ONE launch: partial moments -> grid barrier -> every CTA finishes the statistics of ITS sample -> normalise.  Every CTA of the
+// grid is resident at once (the host caps the grid at the occupancy of this kernel), so a CTA may wait on the generation word
+// that the last arriver bumps.  After the barrier each CTA folds the per-CTA partials of its own sample itself (G x nchunk
+// values from L2, a coalesced microsecond) and keeps (mean, rstd) in shared memory; the first design let the last CTA reduce
+// everything, write coef[] and only then release the grid -- 6 us of serial work plus a global round trip in front of the
+// normalise pass of all 296 CTAs (profiles/r2_gn_trace.txt).  Then each CTA normalises the pixels it has just read (L1 / L2
+// hits: one HBM read and one write per element, one launch instead of two).  Exchange modes: the last arriver also publishes
+// this rank's statistics to the patch group (synchronous mode: before anything else -- the peers wait for them).
 __global__ void __launch_bounds__(512, 2) gn_fused_kernel(const __half* __restrict__ x, const __half* __restrict__ addend, int64_t addend_pitch,
                                                           __half* __restrict__ y, const __half* __restrict__ gamma,
                                                           const __half* __restrict__ beta, float2* __restrict__ partial,
-                                                          const float2* __restrict__ coef, int hw, int C, int G, int V,
+                                                          int hw, int C, int G, int V,
                                                           int lanes, int ppc, int silu, GnExchange ex, unsigned int* gen,
                                                           GnHalo halo) {
-  extern __shared__ float2 ch[];
+  extern __shared__ float2 ch[];                         // [lanes][C] moments; after the fold: red[G*tpp] | mine[G] | coef[G]
   __shared__ unsigned int my_gen;
+  __shared__ bool is_last;
   pdl_wait();
   GN_TR(0, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
   if (threadIdx.x == 0) my_gen = ld_volatile_u32(gen);   // read before this CTA's ticket: the bump needs every CTA's ticket
   __syncthreads();
-  const bool last = gn_stats_body<false>(x, addend, addend_pitch, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
-  if (last) {
-    __threadfence();                                     // coef[] (written by this CTA's threads) before the generation bump
-    __syncthreads();
-    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(my_gen + 1u) : "memory");
-    if (ex.mode >= 2) gn_publish_async(ex, ch);          // the other CTAs are normalising already
-  } else {
-    if (threadIdx.x == 0) {
+  gn_stats_body<false>(x, addend, addend_pitch, partial, hw, C, G, V, lanes, ppc, ex, ch, true);
+  // ---- grid barrier: ticket, the last arriver resets it and bumps the generation
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ex.ticket, 1u);
+    is_last = (t == (unsigned int)ex.nchunk_total - 1);
+    if (is_last) {
+      *ex.ticket = 0;
+      __threadfence();
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gen), "r"(my_gen + 1u) : "memory");
+    } else {
       unsigned int v;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(gen) : "memory");
-        if (v == my_gen) __nanosleep(40);
+        if (v == my_gen) __nanosleep(20);
       } while (v == my_gen);
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  GN_TR(2, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  const int tpp = max(1, min((int)blockDim.x / G, 16));
+  float2* red = ch;
+  float2* mine = ch + G * tpp;
+  float2* coef_s = mine + G;
+  const int nchunk = gridDim.x, b = blockIdx.y;
+  if (is_last && ex.mode == 1) gn_publish_all(ex, partial, G, nchunk, red, mine);     // the peers (and this rank's CTAs) wait for it
+  gn_reduce_sample(partial, b, G, nchunk, ex.inv_ne, red, mine);
+  GN_TR(3, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  gn_coef_sample(ex, b, G, mine, coef_s);
+  GN_TR(4, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
+  if (is_last && ex.mode >= 2) {                         // next step's statistics: only this CTA is late for its normalise pass
+    float2* red2 = coef_s + G;                           // keep coef_s: scratch behind it (host sizes smem for both)
+    gn_publish_all(ex, partial, G, nchunk, red2, red2 + G * tpp);
   }
   GN_TR(5, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
-  gn_apply_body<false>(x, addend, addend_pitch, y, gamma, beta, coef, hw, C, G, V, lanes, ppc, silu, halo);
+  gn_apply_body<false>(x, addend, addend_pitch, y, gamma, beta, coef_s - (size_t)b * G, hw, C, G, V, lanes, ppc, silu, halo);
   GN_TR(6, blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0);
-  GN_TR(7, last && threadIdx.x == 0);
+  GN_TR(7, is_last && threadIdx.x == 0);
 }
 
 #ifdef DF_GN_TRACE
@@ -478,6 +573,11 @@ int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, int64_t ad
   ex.tensor_off = tensor_off; ex.slot_bytes = slot_bytes; ex.group_mask = group_mask;
   size_t smem = (size_t)p.lanes * C * sizeof(float2);           // <= 32 KiB (lanes * C <= 4096)
   if (smem < (size_t)b * groups * sizeof(float2)) smem = (size_t)b * groups * sizeof(float2);
+  {                                                             // fused kernel, after the fold: 2 x (red[G*tpp] + mine[G]) + coef[G]
+    int tpp = p.threads / groups; if (tpp > 16) tpp = 16; if (tpp < 1) tpp = 1;
+    const size_t need = (size_t)(2 * (groups * tpp + groups) + groups) * sizeof(float2);
+    if (smem < need) smem = need;
+  }
   // one launch when the whole grid is resident at once (always, for the plans of gn_plan on a B200: <= 2 CTAs per SM)
   static int fused_capacity = -1;
   if (fused_capacity < 0) {
@@ -491,7 +591,7 @@ int groupnorm_impl(df_comm_t comm, const void* x, const void* addend, int64_t ad
   if (p.nchunk * b <= fused_capacity && smem <= 32 * 1024) {
     unsigned int* gen = ticket + 1;
     DF_CHECK_CUDA(launch_pdl(PDL_GN, gn_fused_kernel, dim3(p.nchunk, b), dim3(p.threads), smem, st, (const __half*)x, (const __half*)addend, addend_pitch,
-                             (__half*)y, (const __half*)gamma, (const __half*)beta, partial, (const float2*)coef, hw, C, groups, p.V,
+                             (__half*)y, (const __half*)gamma, (const __half*)beta, partial, hw, C, groups, p.V,
                              p.lanes, p.ppc, fuse_silu, ex, gen, halo));
     return 0;
   }

@@ -9,8 +9,8 @@ import torch  # noqa: E402
 from distrifuser_b200 import _lib  # noqa: E402
 
 L = _lib.lib()
-names = ["start->stats loop done", "fold+partial+ticket", "(last CTA) ticket->exchange start", "exchange (reduce partials, coef)",
-         "hand-over seen by CTA 0 after coef", "apply (CTA 0)"]
+names = ["start->stats loop done", "fold + partial + grid barrier", "reduce own sample's partials", "coef (+ peer wait)",
+         "publish (last arriver only)", "apply (CTA 0)"]
 for (Cc, hh, ww) in [(320, 128, 128), (640, 64, 64), (1280, 32, 32)]:
     b, G = 2, 32
     x = torch.randn(b, Cc, hh, ww, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
@@ -26,5 +26,5 @@ for (Cc, hh, ww) in [(320, 128, 128), (640, 64, 64), (1280, 32, 32)]:
     buf = (C.c_ulonglong * 16)()
     L.df_debug_gn_trace(buf)
     t = [buf[i] for i in range(8)]
-    d = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]]
+    d = [t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5]]    # slots: see GN_TR in gn_fused_kernel
     print(f"C={Cc} {hh}x{ww}: " + "  ".join(f"{n}: {v / 1e3:.1f} us" for n, v in zip(names, d)) + f"   | CTA0 total {(t[6] - t[0]) / 1e3:.1f} us, last CTA end {(t[7] - t[0]) / 1e3:.1f} us")

@@ -41,9 +41,8 @@ struct __align__(1024) SmemT {
   __half q[NBLK][BM * HB];
   __half k[KSTAGES][NBLK][BN * HB];
   __half v[VSTAGES][NBLK][BN * HB];
-  float red_max[2][2][BM];   // [tile parity][column half][row]: partial row maxima exchanged between the two half-row warps
-  float red_sum[2][BM];      // [column half][row]: partial row sums, combined once in the epilogue (v3: [0][row] = row sum)
-  float red_ref[2][BM];      // v3: exponent reference of every row for the epilogue / split-KV partials ([unit parity][row])
+  float red_sum[2][BM];      // [unit parity][row]: row sums for the epilogue
+  float red_ref[2][BM];      // [unit parity][row]: exponent reference of every row (log2 units) for the epilogue / split-KV partials
   uint64_t q_full, q_empty;   // Q tile of the current work unit loaded / no longer read by the tensor core
   uint64_t k_full[KSTAGES], k_empty[KSTAGES], v_full[VSTAGES], v_empty[VSTAGES];
   uint64_t s_full;
@@ -51,6 +50,12 @@ struct __align__(1024) SmemT {
   uint64_t p_full;
   uint64_t pv_done;
   uint64_t o_free;            // the epilogue of the previous work unit has pulled O out of TMEM
+  uint64_t sched_full[2];     // work-item ring: the TMA lane (scheduler) publishes the next item code, the other roles consume it
+  int sched_code[2];
+  int replay_code[8];         // items whose speculative pass overflowed fp32 (softmax thread 0 -> scheduler), re-run exactly
+  uint32_t replay_wr;
+  uint32_t items_done;        // items whose verdict (clean / replay) has been published by the softmax warps
+  int poison[4];              // [item & 3]: set by any softmax warp that had to give up on the item
   uint32_t tmem_base;
   uint32_t ticket;            // arrival ticket of this part among the parts of its left-over unit
 };
@@ -62,7 +67,10 @@ template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; sta
 // work schedule of one launch (host: plan_schedule): every CTA takes `a` whole units; the R left-over units are cut into P parts
 struct Sched {
   int a, R, P;
+  int dyn;      // 1: whole units are handed out by an atomic ticket counter (grids that fill the SMs); 0: static list per CTA
+  int units;
 };
+constexpr int ITEM_END = -1, ITEM_EXACT = 1 << 30, ITEM_MASK = ITEM_EXACT - 1;
 
 __device__ __forceinline__ float2 ld_f2(const float2* p) {          // coherent load (partials were written during this launch)
   float2 r;
@@ -99,7 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, Cfg<NBLK>::CTAS)
 fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv_own,
                 const CUtensorMap* __restrict__ kvmaps, df_comm_t comm, SegInfo segs, __half* __restrict__ out, int lq,
                 int lseg, int heads, int d, int64_t o_pitch, int nseg, int own_seg, int idx, int wait_flags,
-                float scale_log2, Sched sched, float* part_o, float2* part_ml, unsigned int* part_cnt) {
+                float scale_log2, Sched sched, float* part_o, float2* part_ml, unsigned int* part_cnt, unsigned int* sched_ctr) {
   constexpr int KSTAGES = Cfg<NBLK>::KST, VSTAGES = Cfg<NBLK>::VST;
   constexpr uint32_t TMEM_COLS = Cfg<NBLK>::TMEM, TILE_BYTES = NBLK * BLK_BYTES;
   using Smem = SmemT<NBLK, KSTAGES, VSTAGES>;
@@ -119,11 +127,16 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const int nqt = (lq + BM - 1) / BM;
   const int tps = (lseg + BN - 1) / BN;  // tiles per segment
   const int T_all = nseg * tps;
-  const int n_items = sched.a + ((int)blockIdx.x < sched.R * sched.P ? 1 : 0);
-  // item `it` of this CTA -> Q tile origin, head, batch, first K/V tile, tile count, partial slot (-1: whole unit), left-over index
-  auto get_item = [&](int it, int& q0, int& head, int& bat, int& j_begin, int& T, int& slot, int& lo) {
+  const int n_items = sched.a + ((int)blockIdx.x < sched.R * sched.P ? 1 : 0);     // static schedule only
+  // item code (from the ring, see the scheduler in the TMA lane) -> Q tile origin, head, batch, first K/V tile, tile count,
+  // partial slot (-1: whole unit), left-over index.  Dynamic schedule: the code is the unit; static: the index into this
+  // CTA's list (`a` whole units, then at most one part of a left-over unit).  ITEM_EXACT marks a replay.
+  auto decode = [&](int code, int& q0, int& head, int& bat, int& j_begin, int& T, int& slot, int& lo) {
+    const int it = code & ITEM_MASK;
     int u;
-    if (it < sched.a) {
+    if (sched.dyn) {
+      u = it; j_begin = 0; T = T_all; slot = -1; lo = -1;
+    } else if (it < sched.a) {
       u = it * (int)gridDim.x + (int)blockIdx.x; j_begin = 0; T = T_all; slot = -1; lo = -1;
     } else {
       lo = (int)blockIdx.x / sched.P;
@@ -138,6 +151,11 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     bat = rest / heads;
     q0 = qt * BM;
   };
+  // consumer side of the item ring (MMA lane, softmax warps): code of the ui-th item of this CTA, ITEM_END after the last
+  auto fetch = [&](uint32_t ui) -> int {
+    mbar_wait(&sm.sched_full[ui & 1u], (ui >> 1) & 1u);
+    return *(volatile int*)&sm.sched_code[ui & 1u];
+  };
 
   if (warp == WARP_MMA && lane == 0) {
     mbar_init(&sm.q_full, 1);
@@ -149,6 +167,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(&sm.s_free, NSOFTMAX_WARPS);
     mbar_init(&sm.p_full, NSOFTMAX_WARPS);
     mbar_init(&sm.pv_done, 1);
+    mbar_init(&sm.sched_full[0], 1);
+    mbar_init(&sm.sched_full[1], 1);
+    sm.replay_wr = 0; sm.items_done = 0;
+    sm.poison[0] = sm.poison[1] = sm.poison[2] = sm.poison[3] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == WARP_TMA) {
@@ -168,11 +190,52 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       prefetch_tmap(&tm_kv_own);
       uint32_t rd = 0;
       if (nseg > 1) rd = comm.clock[1];
-      uint32_t g = 0, ui = 0;                              // K/V tiles and work units issued so far by this CTA
-      for (int it = 0; it < n_items; ++it, ++ui) {
+      // ---- SCHEDULER.  This lane decides what the CTA works on next and tells the other roles through a two-entry ring
+      // (sched_code / sched_full).  Grids that fill the SMs draw whole units from an atomic ticket counter: a CTA that starts
+      // late -- its SM slot was held by a publication kernel of the communication stream -- or runs slower simply takes
+      // fewer units, where the static list made the whole grid wait for it (profiles/r2_exposed_comm_n8.txt).  Small grids
+      // keep their static one-item list (a part of a split unit).  Items that the softmax warps had to abandon (fp32
+      // overflow of the speculative exponent reference, see below) come back through replay_code and are re-run with the
+      // row maxima first; the lane only ends the CTA once every published item has a verdict.
+      int it_static = 0;
+      // raw ticket of the next fresh item, drawn one item ahead: the atomic's latency hides under this item's loads (the
+      // value is only looked at when the item is scheduled)
+      auto draw = [&]() -> unsigned int {
+        if (sched.dyn) return atomicAdd(sched_ctr, 1u);
+        return (unsigned int)it_static++;
+      };
+      const unsigned int n_fresh = sched.dyn ? (unsigned int)sched.units : (unsigned int)n_items;
+      unsigned int next_t = draw();
+      bool fresh_left = true;
+      uint32_t replay_rd = 0;
+      uint32_t g = 0, ui = 0;                              // K/V tiles and work items issued so far by this CTA
+      for (;; ++ui) {
+        int code;
+        for (;;) {
+          if (replay_rd != *(volatile uint32_t*)&sm.replay_wr) {
+            code = *(volatile int*)&sm.replay_code[replay_rd & 7u] | ITEM_EXACT;
+            ++replay_rd;
+            break;
+          }
+          if (fresh_left) {
+            if (next_t < n_fresh) { code = (int)next_t; next_t = draw(); break; }
+            fresh_left = false;                            // this CTA's one failing draw
+            if (sched.dyn && next_t == n_fresh + gridDim.x - 1u) *sched_ctr = 0u;   // last draw of the launch: self-resetting
+          }
+          if (*(volatile uint32_t*)&sm.items_done == ui) {   // every published item has its verdict ...
+            __threadfence_block();
+            if (replay_rd != *(volatile uint32_t*)&sm.replay_wr) continue;   // ... and the last one asked for a replay
+            code = ITEM_END;
+            break;
+          }
+          __nanosleep(200);
+        }
+        mbar_wait(&sm.q_empty, (ui & 1u) ^ 1u);            // every Q K^T of the previous item has completed: its ring
+        *(volatile int*)&sm.sched_code[ui & 1u] = code;    // entry (item ui - 2's slot) has been read by every role
+        mbar_arrive(&sm.sched_full[ui & 1u]);
+        if (code == ITEM_END) break;
         int q0, head, bat, j_begin, T, slot, lo;
-        get_item(it, q0, head, bat, j_begin, T, slot, lo);
-        mbar_wait(&sm.q_empty, (ui & 1u) ^ 1u);            // every Q K^T of the previous item has completed
+        decode(code, q0, head, bat, j_begin, T, slot, lo);
         mbar_expect_tx(&sm.q_full, TILE_BYTES);
 #pragma unroll
         for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sm.q[blk], &tm_q, &sm.q_full, blk * HB, head, q0, bat);
@@ -221,10 +284,12 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_commit(&sm.k_empty[st]);
         tc_commit(&sm.s_full);
       };
-      uint32_t g = 0, ui = 0;                              // K/V tiles and work units consumed so far by this CTA
-      for (int it = 0; it < n_items; ++it, ++ui) {
+      uint32_t g = 0, ui = 0;                              // K/V tiles and work items consumed so far by this CTA
+      for (;; ++ui) {
+        const int code = fetch(ui);
+        if (code == ITEM_END) break;
         int q0, head, bat, j_begin, T, slot, lo;
-        get_item(it, q0, head, bat, j_begin, T, slot, lo);
+        decode(code, q0, head, bat, j_begin, T, slot, lo);
         mbar_wait(&sm.q_full, ui & 1u);
         if (g > 0) {                                       // S still holds the last tile of the previous unit until the
           mbar_wait(&sm.s_free, (g - 1) & 1u);             // softmax warps have pulled it into registers
@@ -280,12 +345,17 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #endif
 #define DF_BAR(member) (bars + (uint32_t)(offsetof(Smem, member) - offsetof(Smem, q_full)))
     const int c4 = lane & 3, r8 = lane >> 2;
-    constexpr bool HOLD_S = Cfg<NBLK>::CTAS == 2;                  // see "speculative exponent reference" below
-    uint32_t g = 0, ui = 0;                                        // K/V tiles / work units processed so far by this CTA (barrier phases)
-    for (int it = 0; it < n_items; ++it, ++ui) {
+    constexpr bool SPECULATE = Cfg<NBLK>::CTAS == 2;               // see "speculative exponent reference" below
+    uint32_t g = 0, ui = 0;                                        // K/V tiles / work items processed so far by this CTA (barrier phases)
+    for (;; ++ui) {
+    const int code = fetch(ui);
+    if (code == ITEM_END) break;
     int q0, head, bat, j_begin, T, slot, lo;
-    get_item(it, q0, head, bat, j_begin, T, slot, lo);
-    float m_refA = -INFINITY, m_refB = -INFINITY;                  // exponent references of rows rA / rB (raw S units)
+    decode(code, q0, head, bat, j_begin, T, slot, lo);
+    const bool exact_item = !SPECULATE || (code & ITEM_EXACT) != 0;
+    bool poisoned = false;                                         // warp-uniform: this warp gave up on the item (replay)
+    // exponent references of rows rA / rB, kept NEGATED and in log2 units: P = 2^(S * scale_log2 + n)
+    float nA = INFINITY, nB = INFINITY;
     float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
     int t = j_begin % tps;
     for (int j = 0; j < T; ++j, ++t, ++g) {
@@ -294,100 +364,115 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_wait(DF_BAR(s_full), g & 1u);
       tc_fence_after();
       if (threadIdx.x == 0) DF_TR(0, g);
-      // SPECULATIVE EXPONENT REFERENCE (HOLD_S, the two-CTAs-per-SM configuration).  Only the first tile of a unit computes the
-      // row maxima before its exponentials.  Every later tile exponentiates against the reference it inherited -- no FMNMX
-      // pass, no quad shuffles, no max -> exp dependency -- and then proves the guess was harmless: P is stored as fp16, so it
-      // is enough that no value reached 2^13, which the row sums the tile needs anyway show (a thread's 32 values of a row sum
-      // to more than 2^13 only if one of them exceeded 2^8; the polynomial lanes, whose exponent insertion wraps for x >= 128,
-      // are covered by the largest integer part they produced).  S_j stays in TMEM until the check has passed, so the rare
-      // failing tile is simply loaded again and redone the classic way (maxima first, O and l rescaled).  The price is that
-      // Q K_{j+1}^T is issued after the exponentials of tile j instead of under them; it still runs under the fp16 packing,
-      // the P store and the other CTA's softmax.
-#ifdef DF_EXPERIMENT_EARLY_RELEASE     // timing experiment only (no redo possible): what holding S costs
-      constexpr bool RELEASE_EARLY = true;
-      bool exact = j == 0;
-#else
-      constexpr bool RELEASE_EARLY = !HOLD_S;
-      bool exact = !HOLD_S || j == 0;
-#endif
-      bool moved = false;
-      float alphaA = 1.f, alphaB = 1.f, tA, tB;
       uint32_t sr[64];
-      for (;;) {
-        tmem_ld_16x256b_x16(lane_base + COL_S, sr);
-        tmem_wait_ld();
-        if (RELEASE_EARLY) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(DF_BAR(s_free));      // the tensor core may overwrite S with Q K_{j+1}^T now
-        }
-        if (threadIdx.x == 0) DF_TR(1, g);
-        if (valid < BN) {                              // ragged last tile of a segment only (warp-uniform branch)
-          asm volatile("" ::: "memory");
+      tmem_ld_16x256b_x16(lane_base + COL_S, sr);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(DF_BAR(s_free));      // the tensor core may overwrite S with Q K_{j+1}^T now
+      if (threadIdx.x == 0) DF_TR(1, g);
+      if (valid < BN) {                                // ragged last tile of a segment only (warp-uniform branch)
+        asm volatile("" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 16; ++i)
 #pragma unroll
-            for (int k = 0; k < 2; ++k)
-              if (8 * i + 2 * c4 + k >= valid) { sr[4 * i + k] = 0xff800000u; sr[4 * i + 2 + k] = 0xff800000u; }
-        }
-        if (exact) {
-          float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
+          for (int k = 0; k < 2; ++k)
+            if (8 * i + 2 * c4 + k >= valid) { sr[4 * i + k] = 0xff800000u; sr[4 * i + 2 + k] = 0xff800000u; }
+      }
+      // SPECULATIVE EXPONENT REFERENCE (two-CTAs-per-SM configuration).  Only the first tile of an item computes the row maxima
+      // before its exponentials.  Every later tile exponentiates against the reference it inherited -- no FMNMX pass, no quad
+      // shuffles, no max -> exp dependency -- and then proves the guess was harmless: P is stored as fp16, so it is enough
+      // that no value reached 2^13, which the row sums the tile needs anyway show (a thread's 32 values of a row sum to more
+      // than 2^13 only if one of them exceeded 2^8; the polynomial lanes, whose exponent insertion wraps for x >= 128, are
+      // covered by the largest integer part they produced).  S has long been released by then; a failing tile is repaired
+      // IN REGISTERS: the exponentials are still exact fp32 values, so their row maxima give the new reference as a power
+      // of two and P, l, O are rescaled by it -- no second look at S.  Only when an exponential overflowed fp32 itself (a logit
+      // 88 nats above the reference) is the information gone: the warp marks the item poisoned, the CTA finishes it without
+      // publishing anything and the scheduler re-runs it with the maxima first (ITEM_EXACT).
+      const bool exact = exact_item || j == 0;
+      bool moved = false;
+      float alphaA = 1.f, alphaB = 1.f;
+      if (exact) {
+        float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            mA0 = max3(mA0, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
-            mB0 = max3(mB0, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
-            mA1 = max3(mA1, __uint_as_float(sr[4 * i + 4]), __uint_as_float(sr[4 * i + 5]));
-            mB1 = max3(mB1, __uint_as_float(sr[4 * i + 6]), __uint_as_float(sr[4 * i + 7]));
-          }
-          float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
-          mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
-          mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
-          mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
-          mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
-          if (threadIdx.x == 0) DF_TR(2, g);
-          // lazy rescale: keep the old reference while the max moved by < 2^8
-          if ((mA - m_refA) * scale_log2 > 8.f) { alphaA = ex2((m_refA - mA) * scale_log2); m_refA = mA; lA *= alphaA; moved = true; }
-          if ((mB - m_refB) * scale_log2 > 8.f) { alphaB = ex2((m_refB - mB) * scale_log2); m_refB = mB; lB *= alphaB; moved = true; }
+        for (int i = 0; i < 16; i += 2) {
+          mA0 = max3(mA0, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
+          mB0 = max3(mB0, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
+          mA1 = max3(mA1, __uint_as_float(sr[4 * i + 4]), __uint_as_float(sr[4 * i + 5]));
+          mB1 = max3(mB1, __uint_as_float(sr[4 * i + 6]), __uint_as_float(sr[4 * i + 7]));
         }
-        const float nA = -m_refA * scale_log2, nB = -m_refB * scale_log2;
-        const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
-        uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
-        float tmax = 0.f;                              // largest (1.5 * 2^23 + integer part) of the polynomial lanes
+        float mA = fmaxf(mA0, mA1), mB = fmaxf(mB0, mB1);
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 1));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 1));
+        mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, 2));
+        mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, 2));
+        if (threadIdx.x == 0) DF_TR(2, g);
+        // lazy rescale: keep the old reference while the max moved by < 2^8
+        const float dA = fmaf(mA, scale_log2, nA), dB = fmaf(mB, scale_log2, nB);      // log2 of the largest P of the tile
+        if (dA > 8.f) { alphaA = ex2(-dA); nA = -mA * scale_log2; lA *= alphaA; moved = true; }
+        if (dB > 8.f) { alphaB = ex2(-dB); nB = -mB * scale_log2; lB *= alphaB; moved = true; }
+      }
+      const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
+      uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
+      float tmax = 0.f;                                // largest (1.5 * 2^23 + integer part) of the polynomial lanes
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {                 // exponentials IN PLACE (fp32): nothing leaves the registers before the check
-          const uint64_t xA = fma2(pack2(__uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1])), scale2, nA2);
-          const uint64_t xB = fma2(pack2(__uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3])), scale2, nB2);
-          float a0, a1, b0, b1;
-          if ((i * DF_EMU_GROUPS) / 16 != ((i + 1) * DF_EMU_GROUPS) / 16) {             // this share of the exponentials runs on the FMA / ALU pipes
-            ex2_poly2(xA, a0, a1, tmax);
-            ex2_poly2(xB, b0, b1, tmax);
-          } else {
-            float x0, x1;
-            unpack2(xA, x0, x1); a0 = ex2(x0); a1 = ex2(x1);
-            unpack2(xB, x0, x1); b0 = ex2(x0); b1 = ex2(x1);
-          }
-          sA = add2(sA, pack2(a0, a1));
-          sB = add2(sB, pack2(b0, b1));
-          sr[4 * i] = __float_as_uint(a0); sr[4 * i + 1] = __float_as_uint(a1);
-          sr[4 * i + 2] = __float_as_uint(b0); sr[4 * i + 3] = __float_as_uint(b1);
+      for (int i = 0; i < 16; ++i) {                   // exponentials IN PLACE (fp32): nothing leaves the registers before the check
+        const uint64_t xA = fma2(pack2(__uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1])), scale2, nA2);
+        const uint64_t xB = fma2(pack2(__uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3])), scale2, nB2);
+        float a0, a1, b0, b1;
+        if ((i * DF_EMU_GROUPS) / 16 != ((i + 1) * DF_EMU_GROUPS) / 16) {             // this share of the exponentials runs on the FMA / ALU pipes
+          ex2_poly2(xA, a0, a1, tmax);
+          ex2_poly2(xB, b0, b1, tmax);
+        } else {
+          float x0, x1;
+          unpack2(xA, x0, x1); a0 = ex2(x0); a1 = ex2(x1);
+          unpack2(xB, x0, x1); b0 = ex2(x0); b1 = ex2(x1);
         }
-        {
-          float s0, s1;
-          unpack2(sA, s0, s1); tA = s0 + s1;
-          unpack2(sB, s0, s1); tB = s0 + s1;
-        }
-        if (exact) break;
+        sA = add2(sA, pack2(a0, a1));
+        sB = add2(sB, pack2(b0, b1));
+        sr[4 * i] = __float_as_uint(a0); sr[4 * i + 1] = __float_as_uint(a1);
+        sr[4 * i + 2] = __float_as_uint(b0); sr[4 * i + 3] = __float_as_uint(b1);
+      }
+      float tA, tB;
+      {
+        float s0, s1;
+        unpack2(sA, s0, s1); tA = s0 + s1;
+        unpack2(sB, s0, s1); tB = s0 + s1;
+      }
+      if (!exact) {
         const bool over = !(tA <= 8192.f) || !(tB <= 8192.f) || tmax > 12582912.f + 13.f;   // also true for NaN sums
-        if (!__any_sync(0xffffffffu, over)) break;
-        exact = true;                                  // rare: redo this tile with the maxima first
+        if (__any_sync(0xffffffffu, over)) {           // rare: the inherited reference was too small for this tile
+          const bool lost = !(tA < 3.0e38f) || !(tB < 3.0e38f) || tmax > 12582912.f + 126.f;
+          if (__any_sync(0xffffffffu, lost)) {
+            poisoned = true;                           // fp32 overflow: only S could tell the values apart, and S is gone
+          } else {
+            float pA = 0.f, pB = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              pA = max3(pA, __uint_as_float(sr[4 * i]), __uint_as_float(sr[4 * i + 1]));
+              pB = max3(pB, __uint_as_float(sr[4 * i + 2]), __uint_as_float(sr[4 * i + 3]));
+            }
+            pA = fmaxf(pA, __shfl_xor_sync(0xffffffffu, pA, 1)); pB = fmaxf(pB, __shfl_xor_sync(0xffffffffu, pB, 1));
+            pA = fmaxf(pA, __shfl_xor_sync(0xffffffffu, pA, 2)); pB = fmaxf(pB, __shfl_xor_sync(0xffffffffu, pB, 2));
+            // shift the reference by the exponent of the row maximum (rows that stayed below 2 keep theirs): exact powers of two
+            const int kA = max(0, (int)((__float_as_uint(pA) >> 23) & 0xffu) - 127), kB = max(0, (int)((__float_as_uint(pB) >> 23) & 0xffu) - 127);
+            alphaA = __uint_as_float((uint32_t)(127 - kA) << 23);
+            alphaB = __uint_as_float((uint32_t)(127 - kB) << 23);
+            nA -= (float)kA; nB -= (float)kB;
+            lA *= alphaA; lB *= alphaB; tA *= alphaA; tB *= alphaB;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              sr[4 * i] = __float_as_uint(__uint_as_float(sr[4 * i]) * alphaA);
+              sr[4 * i + 1] = __float_as_uint(__uint_as_float(sr[4 * i + 1]) * alphaA);
+              sr[4 * i + 2] = __float_as_uint(__uint_as_float(sr[4 * i + 2]) * alphaB);
+              sr[4 * i + 3] = __float_as_uint(__uint_as_float(sr[4 * i + 3]) * alphaB);
+            }
+            moved = true;
+          }
+        }
       }
       lA += tA;
       lB += tB;
-      if (!RELEASE_EARLY) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(DF_BAR(s_free));        // the tensor core may overwrite S with Q K_{j+1}^T now
-      }
       if (threadIdx.x == 0) DF_TR(3, g);
       // P -> fp16 -> TMEM in two halves of 32 packed columns (16 instead of 32 packed registers live at a time)
 #pragma unroll
@@ -403,7 +488,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);  // P buffer free, O quiescent
           tc_fence_after();
           if (threadIdx.x == 0) DF_TR(4, g);
-          if (exact && __any_sync(0xffffffffu, moved)) {     // rare: rescale this warp's 16 rows of O
+          if (__any_sync(0xffffffffu, moved)) {              // rare: rescale this warp's 16 rows of O
 #pragma unroll
             for (int blk = 0; blk < NBLK; ++blk) {
               uint32_t o[32];
@@ -434,9 +519,22 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     lA += __shfl_xor_sync(0xffffffffu, lA, 2); lB += __shfl_xor_sync(0xffffffffu, lB, 2);
     if (c4 == 0) {
       sm.red_sum[ui & 1][lane16 + r8] = lA; sm.red_sum[ui & 1][lane16 + r8 + 8] = lB;
-      sm.red_ref[ui & 1][lane16 + r8] = m_refA; sm.red_ref[ui & 1][lane16 + r8 + 8] = m_refB;
+      sm.red_ref[ui & 1][lane16 + r8] = -nA; sm.red_ref[ui & 1][lane16 + r8 + 8] = -nB;
     }
+    if (SPECULATE && poisoned && lane == 0) sm.poison[ui & 3u] = 1;
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    const bool item_bad = SPECULATE && *(volatile int*)&sm.poison[ui & 3u] != 0;
+    if (threadIdx.x == 0) {                           // verdict for the scheduler: replay request, then the done counter
+      sm.poison[(ui + 2u) & 3u] = 0;                  // the entry two items ahead (nobody reads or sets it now)
+      if (item_bad) {
+        const uint32_t wr = sm.replay_wr;
+        *(volatile int*)&sm.replay_code[wr & 7u] = code & ITEM_MASK;
+        __threadfence_block();
+        *(volatile uint32_t*)&sm.replay_wr = wr + 1u;
+      }
+      __threadfence_block();
+      *(volatile uint32_t*)&sm.items_done = ui + 1u;
+    }
     const int half = hr;
     const int row = quad * 32 + lane;
     const uint32_t row_base = tmem + ((uint32_t)(quad * 32) << 16);
@@ -444,7 +542,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const float m_ref = sm.red_ref[ui & 1][row];
     mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);
     tc_fence_after();
-    const bool partial = slot >= 0;
+    const bool partial = slot >= 0 && !item_bad;     // a poisoned item publishes nothing: its replay will
     const int64_t prow = (int64_t)(partial ? slot : 0) * BM + row;          // row of this part's partial in the workspace
     if (partial && half == 0) part_ml[prow] = make_float2(m_ref, l_row);
     uint32_t o[NBLK][32];
@@ -454,7 +552,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tc_fence_before();                                // O is in registers: the next item's first P V may overwrite the accumulator
     __syncwarp();
     if (lane == 0) mbar_arrive(DF_BAR(o_free));
-    bool finish = !partial;                           // this CTA writes the output rows
+    bool finish = !partial && !item_bad;              // this CTA writes the output rows
     float m_all = m_ref, denom = l_row, w_own = 1.f;
     if (partial) {
       // ---- un-normalised fp32 partial (reference max m_ref) -> workspace; the last part of this unit to arrive merges
@@ -488,7 +586,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int c = 0; c < 32; ++c) o[blk][c] = 0u;
         for (int pp = 0; pp < sched.P; ++pp) {
           const float2 ml = ld_f2(part_ml + (int64_t)(s0 + pp) * BM + row);
-          const float w = ex2((ml.x - m_max) * scale_log2);
+          const float w = ex2(ml.x - m_max);          // references are kept in log2 units
           denom = fmaf(w, ml.y, denom);
 #pragma unroll
           for (int blk = 0; blk < NBLK; ++blk) {
@@ -609,29 +707,33 @@ int sm_count() {
 // not pay -- the R CTAs of the last round have their SMs to themselves and run ~1.6x faster per tile, which a balanced tail
 // trades for partial writes and a merge (SDXL 1024^2: level 1 144 vs 136 us, level 2 32.5 vs 30.4 us) -- so P > 1 only when the
 // units leave at least half of the CTA slots idle AND every part keeps >= 8 K/V tiles (n = 4 level 1: 41.6 -> 37.7 us).
-void plan_schedule(int b, int lq, int lseg, int nseg, int heads, int d, bool allow_split, int& grid, Sched& sc) {
+void plan_schedule(int b, int lq, int lseg, int nseg, int heads, int d, bool have_ws, int& grid, Sched& sc) {
   const int nblk = (d + HB - 1) / HB;
   const long long slots = (long long)sm_count() * (nblk == 1 ? Cfg<1>::CTAS : 1);
   const long long units = (long long)((lq + BM - 1) / BM) * heads * b;
   const int t_all = nseg * ((lseg + BN - 1) / BN);
+  sc.units = (int)units;
   if (units >= slots) {
     grid = (int)slots;
     sc.a = (int)(units / slots);
     sc.R = (int)(units % slots);
     sc.P = 1;
+    sc.dyn = have_ws ? 1 : 0;                          // the ticket counter lives in the workspace
   } else {
-    long long p = allow_split ? slots / units : 1;
+    long long p = have_ws ? slots / units : 1;
     if (p > t_all / DF_MIN_PART_TILES) p = t_all / DF_MIN_PART_TILES;
     if (p < 1) p = 1;
-    sc.a = 0; sc.R = (int)units; sc.P = (int)p;
+    sc.a = 0; sc.R = (int)units; sc.P = (int)p; sc.dyn = 0;
     grid = (int)(units * p);
   }
 }
+// workspace: [1 KiB header: ticket counter of the dynamic schedule] [arrival tickets of split units] [partials (m, l)] [partials O]
+constexpr size_t WS_HEADER = 1024;
 size_t workspace_need(const Sched& sc, int d) {
-  if (sc.P <= 1) return 0;
+  if (sc.P <= 1) return WS_HEADER;
   const size_t hd_pad = (size_t)((d + HB - 1) / HB) * HB;
   const size_t parts = (size_t)sc.R * sc.P;
-  return 1024 + ((size_t)sc.R * sizeof(unsigned int) + 255) / 256 * 256 + parts * BM * sizeof(float2) + parts * BM * hd_pad * sizeof(float);
+  return WS_HEADER + 1024 + ((size_t)sc.R * sizeof(unsigned int) + 255) / 256 * 256 + parts * BM * sizeof(float2) + parts * BM * hd_pad * sizeof(float);
 }
 }  // namespace
 
@@ -668,18 +770,19 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
   for (int s = 0; s < DF_MAX_WORLD; ++s) segs.rank[s] = (s < nseg && seg_rank_host) ? seg_rank_host[s] : 0;
   const float sc = (scale > 0.f ? scale : 1.f / sqrtf((float)d)) * 1.4426950408889634f;
   const int nblk = (d + HB - 1) / HB;
-  // work schedule; the left-over split needs a ZERO-INITIALISED workspace of df_attn_workspace_bytes() (it holds the self-resetting
-  // arrival tickets); without one the left-over units are processed whole
+  // work schedule; the dynamic ticket counter and the K/V split of small grids need a ZERO-INITIALISED workspace of
+  // df_attn_workspace_bytes() (self-resetting counters); without one every CTA walks a static list of whole units
   int grid_x;
   Sched sched;
   plan_schedule(b, lq, lseg, nseg, heads, d, true, grid_x, sched);
-  if (sched.P > 1 && (workspace == nullptr || workspace_bytes < workspace_need(sched, d)))
+  if (workspace == nullptr || workspace_bytes < workspace_need(sched, d))
     plan_schedule(b, lq, lseg, nseg, heads, d, false, grid_x, sched);
+  unsigned int* sched_ctr = sched.dyn ? (unsigned int*)workspace : nullptr;
   unsigned int* part_cnt = nullptr;
   float2* part_ml = nullptr;
   float* part_o = nullptr;
   if (sched.P > 1) {
-    char* w = (char*)workspace;
+    char* w = (char*)workspace + WS_HEADER;
     part_cnt = (unsigned int*)w;
     w += ((size_t)sched.R * sizeof(unsigned int) + 255) / 256 * 256;
     part_ml = (float2*)w;
@@ -697,7 +800,7 @@ extern "C" int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, vo
     }                                                                                                                        \
     DF_CHECK_CUDA(launch_pdl(PDL_ATTN, fmha_fwd_kernel<NB>, grid, dim3(NTHREADS), smem_bytes, (cudaStream_t)stream, tq, tkv,           \
                              (const CUtensorMap*)kvmaps, comm, segs, (__half*)out, lq, lseg, heads, d, o_pitch, nseg,        \
-                             own_seg, idx, wait_flags, sc, sched, part_o, part_ml, part_cnt));                               \
+                             own_seg, idx, wait_flags, sc, sched, part_o, part_ml, part_cnt, sched_ctr));                               \
   }
   if (nblk == 1) DF_LAUNCH_FMHA(1) else if (nblk == 2) DF_LAUNCH_FMHA(2) else DF_LAUNCH_FMHA(3)
 #undef DF_LAUNCH_FMHA

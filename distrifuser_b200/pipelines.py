@@ -5,6 +5,8 @@
 `from_pretrained` uses the real diffusers pipelines when the package (and weights) are available.  This image has
 neither, so `from_synthetic` builds the same object around a random-weight UNet of the SDXL / SD1.x architecture
 and a latent-space pipeline stand-in (compat/pipeline.py): that is what bench.py and the parity tests drive."""
+import os
+
 import torch
 
 from .models.distri_sdxl_unet_pp import DistriUNetPP
@@ -85,10 +87,16 @@ class _DistriPipelineBase:
             pool = None
             from . import _lib
             launches = []
+            # the compute kernels are captured on a stream of priority DF_COMPUTE_PRIO (default -1 = above the publication
+            # stream's 0): when a K/V projection finishes, the attention grid that follows it takes the SM slots before the
+            # publication kernel of the same K/V does -- a publication CTA that got there first keeps a persistent attention
+            # CTA out of its SM for the whole transfer (profiles/r2_exposed_comm_n8.txt)
+            prio = int(os.environ.get("DF_COMPUTE_PRIO", "-1"))
+            capture_stream = torch.cuda.Stream(device=cfg.device, priority=prio)
             for counter in counters:
                 graph = torch.cuda.CUDAGraph()
                 n0 = _lib.LAUNCHES["total"]
-                with torch.cuda.graph(graph, pool=pool):
+                with torch.cuda.graph(graph, pool=pool, stream=capture_stream):
                     unet.set_counter(counter)
                     output = unet(**static_inputs, return_dict=False, record=True)[0]
                     static_outputs.append(output)

@@ -12,14 +12,15 @@ from helpers import LoopbackArena, sdpa_ref
 pytestmark = pytest.mark.gpu
 
 
-def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, wait=0):
+def _attn(q, kv, heads, comm=None, maps=None, nseg=1, own=0, idx=0, lseg=None, wait=0, no_ws=False):
     from distrifuser_b200 import _lib
     b, lq, Cq = q.shape
     d = Cq // heads
     out = torch.empty_like(q)
     seg_rank = (C.c_int32 * 8)(*range(8))
     L = _lib.lib()
-    ws_bytes = L.df_attn_workspace_bytes(b, lq, lseg or kv.shape[1], nseg, heads, d)      # > 0: the split-KV path is taken
+    # zeroed scratch: ticket counter of the dynamic schedule, partials of split units (no_ws: static whole-unit lists instead)
+    ws_bytes = 0 if no_ws else L.df_attn_workspace_bytes(b, lq, lseg or kv.shape[1], nseg, heads, d)
     ws = torch.zeros(max(ws_bytes, 1), dtype=torch.uint8, device="cuda")
     _lib.check(L.df_attn_fwd(comm or _lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), maps, b, lq,
                              lseg or kv.shape[1], heads, d, q.stride(1), kv.stride(1), out.stride(1), nseg, own,
@@ -63,15 +64,53 @@ def test_attention_single_segment(b, lq, lk, heads, d):
     assert err < 2e-3, f"max abs err {err}"
 
 
+@pytest.mark.parametrize("b,lq,lk,heads,d,gain", [(2, 2048, 300, 20, 64, 1.0), (2, 1024, 1024, 20, 64, 30.0), (2, 1100, 520, 8, 80, 1.0)])
+def test_attention_static_schedule_without_workspace(b, lq, lk, heads, d, gain):
+    """No workspace: every CTA walks its static list of whole units (and replays the ones a large logit jump poisons)."""
+    torch.manual_seed(3)
+    Cq = heads * d
+    q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16) * (4 if gain > 1 else 1)
+    kv = torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16)
+    kv[:, lk // 2:, :Cq] *= gain
+    out = _attn(q, kv, heads, no_ws=True)
+    ref = sdpa_ref(q, kv[..., :Cq], kv[..., Cq:], heads)
+    err = (out.float() - ref).abs().max().item()
+    assert torch.isfinite(out).all() and err < 4e-3, f"max abs err {err}"
+
+
+def test_attention_workspace_counters_reset_between_launches():
+    """The ticket counter / arrival tickets in the workspace are self-resetting: the same zeroed buffer serves many launches."""
+    from distrifuser_b200 import _lib
+    torch.manual_seed(5)
+    L = _lib.lib()
+    b, lq, lk, heads, d = 2, 1024, 1024, 20, 64
+    Cq = heads * d
+    ws = torch.zeros(L.df_attn_workspace_bytes(b, lq, lk, 1, heads, d), dtype=torch.uint8, device="cuda")
+    seg_rank = (C.c_int32 * 8)(*range(8))
+    for rep in range(3):
+        q = torch.randn(b, lq, Cq, device="cuda", dtype=torch.float16)
+        kv = torch.randn(b, lk, 2 * Cq, device="cuda", dtype=torch.float16)
+        out = torch.empty_like(q)
+        _lib.check(L.df_attn_fwd(_lib.null_comm(), q.data_ptr(), kv.data_ptr(), out.data_ptr(), None, b, lq, lk, heads, d, q.stride(1),
+                                 kv.stride(1), out.stride(1), 1, 0, seg_rank, 0, 0, 0.0, ws.data_ptr(), ws.numel(),
+                                 torch.cuda.current_stream().cuda_stream), "df_attn_fwd")
+        torch.cuda.synchronize()
+        assert int(ws[:4].view(torch.int32).item()) == 0, "ticket counter not reset"
+        ref = sdpa_ref(q, kv[..., :Cq], kv[..., Cq:], heads)
+        assert (out.float() - ref).abs().max().item() < 2e-3
+
+
 def test_attention_tail_split_is_planned():
-    """df_attn_workspace_bytes > 0 exactly when the schedule cuts left-over units into K/V parts."""
+    """df_attn_workspace_bytes: 1 KiB (the ticket counter of the dynamic schedule) unless the schedule also cuts units into K/V
+    parts (small grids), which adds the partials."""
     from distrifuser_b200 import _lib
     L = _lib.lib()
-    assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > 0         # 8 units on 296 slots, 64 K/V tiles
-    assert L.df_attn_workspace_bytes(2, 1024, 1024, 1, 20, 64) == 0      # 320 units fill the 296 slots: left-overs stay whole
-    assert L.df_attn_workspace_bytes(1, 1024, 4096, 1, 10, 64) > 0       # SDXL 1024^2 n=4 level 1: 80 units x 32 tiles -> 3 parts
-    assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == 0        # cross-attention: one K/V tile, nothing to cut
-    assert L.df_attn_workspace_bytes(1, 3600, 3600, 4, 20, 64) == 0      # 580 units: 284 left over on 296 slots -> whole
+    HDR = 1024
+    assert L.df_attn_workspace_bytes(1, 256, 8192, 1, 4, 64) > HDR         # 8 units on 296 slots, 64 K/V tiles
+    assert L.df_attn_workspace_bytes(2, 1024, 1024, 1, 20, 64) == HDR      # 320 units fill the 296 slots: whole units, dynamic tickets
+    assert L.df_attn_workspace_bytes(1, 1024, 4096, 1, 10, 64) > HDR       # SDXL 1024^2 n=4 level 1: 80 units x 32 tiles -> 3 parts
+    assert L.df_attn_workspace_bytes(2, 1024, 77, 1, 20, 64) == HDR        # cross-attention: one K/V tile, nothing to cut
+    assert L.df_attn_workspace_bytes(1, 3600, 3600, 4, 20, 64) == HDR      # 580 units on 296 slots -> whole units
 
 
 @pytest.mark.parametrize("case", ["late_tiles_x6", "late_tiles_x40", "some_rows", "one_polynomial_column", "one_mufu_column",

@@ -30,7 +30,11 @@ constexpr int BM = 128;      // Q rows per CTA
 constexpr int BN = 128;      // K/V rows per tile
 constexpr int HB = 64;       // head-dim block: one 128-byte swizzled row; d is padded to NBLK * 64 columns (TMA zero-fills)
 constexpr int NSOFTMAX_WARPS = 8;
-constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + 2);
+#ifndef DF_FMHA_SETMAXNREG
+#define DF_FMHA_SETMAXNREG 1
+#endif
+constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + (DF_FMHA_SETMAXNREG == 1 ? 4 : 2));   // 3 warpgroups: 2 x softmax, 1 x (TMA warp, MMA warp, two idle warps) -- whole
+                                                      // warpgroups so that setmaxnreg may move registers between them
 constexpr int WARP_TMA = NSOFTMAX_WARPS, WARP_MMA = NSOFTMAX_WARPS + 1;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;   // S fp32 [0,128), P packed fp16 [128,192), O fp32 [192, 192 + 64*NBLK)
 constexpr uint32_t BLK_BYTES = BN * HB * 2;                // one 128 x 64 fp16 block = 16 KiB
@@ -61,6 +65,10 @@ struct __align__(1024) SmemT {
 };
 template <int NBLK> struct Cfg;
 template <> struct Cfg<1> { static constexpr int KST = 3, VST = 2, CTAS = 2; static constexpr uint32_t TMEM = 256; };
+// Two CTAs of 384 threads per SM start at 80 registers per thread (65536 / 768).  The producer warpgroup gives registers back
+// (setmaxnreg.dec 32) and the two softmax warpgroups take them (setmaxnreg.inc 104: 256 x 104 + 128 x 32 = 384 x 80): the softmax
+// loop holds a 64-value S fragment per thread and ran with spills at the 96 registers an even split allows.
+constexpr int REGS_PRODUCER = 32, REGS_SOFTMAX = DF_FMHA_SETMAXNREG == 2 ? 112 : 104;   // (2: experiment, 10 warps = a partial third warpgroup)
 template <> struct Cfg<2> { static constexpr int KST = 2, VST = 2, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 
@@ -183,6 +191,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = sm.tmem_base;
   pdl_wait();                                          // everything above overlapped the tail of the previous kernel
 
+  if (warp >= NSOFTMAX_WARPS) {
+  if (DF_FMHA_SETMAXNREG && Cfg<NBLK>::CTAS == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_PRODUCER));
   if (warp == WARP_TMA) {
     // =============================================================== TMA producer
     if (lane == 0) {
@@ -325,7 +335,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
+  }
   } else {
+    if (DF_FMHA_SETMAXNREG && Cfg<NBLK>::CTAS == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_SOFTMAX));
     // =============================================================== softmax / correction / epilogue (warps 0-7)
     // Warp w owns 16 rows (TMEM lanes 32*(w&3) + 16*(w>>2) ..+15) and ALL 128 S columns of them, in the 16x256b fragment
     // layout: thread t holds rows rA = t/4 and rB = t/4 + 8, columns 8i + 2(t%4) + {0,1} for i = 0..15 (64 values).  A row
@@ -352,8 +364,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (code == ITEM_END) break;
     int q0, head, bat, j_begin, T, slot, lo;
     decode(code, q0, head, bat, j_begin, T, slot, lo);
-    const bool exact_item = !SPECULATE || (code & ITEM_EXACT) != 0;
-    bool poisoned = false;                                         // warp-uniform: this warp gave up on the item (replay)
     // exponent references of rows rA / rB, kept NEGATED and in log2 units: P = 2^(S * scale_log2 + n)
     float nA = INFINITY, nB = INFINITY;
     float lA = 0.f, lB = 0.f;                                      // partial row sums over this thread's columns
@@ -365,7 +375,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       if (threadIdx.x == 0) DF_TR(0, g);
       uint32_t sr[64];
-      tmem_ld_16x256b_x16(lane_base + COL_S, sr);
+      tmem_ld_16x256b_x8(lane_base + COL_S, sr);        // two x8 loads (one x16 exceeds what ptxas accepts under the 80-register
+      tmem_ld_16x256b_x8(lane_base + COL_S + 64, sr + 32);   // launch bound, whatever setmaxnreg grants later), one wait
       tmem_wait_ld();
       tc_fence_before();
       __syncwarp();
@@ -389,9 +400,27 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       // of two and P, l, O are rescaled by it -- no second look at S.  Only when an exponential overflowed fp32 itself (a logit
       // 88 nats above the reference) is the information gone: the warp marks the item poisoned, the CTA finishes it without
       // publishing anything and the scheduler re-runs it with the maxima first (ITEM_EXACT).
-      const bool exact = exact_item || j == 0;
-      bool moved = false;
-      float alphaA = 1.f, alphaB = 1.f;
+      const bool exact = !SPECULATE || (code & ITEM_EXACT) != 0 || j == 0;
+      // O of this warp's 16 rows *= alpha (rare: the reference moved).  Called warp-uniformly; waits for P V_{j-1} first --
+      // the regular wait further down then finds the phase complete.  Keeping this out of the common path also keeps
+      // alpha / moved out of its live registers (the loop runs at the 96-register cap of two CTAs per SM).
+      auto rescale_o = [&](float alphaA, float alphaB) {
+        if (j == 0) return;
+        mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < NBLK * HB; c += 16) {      // 16 columns (8 registers) at a time: S is live around this call
+          uint32_t o[8];
+          tmem_ld_16x256b_x2(lane_base + COL_O + c, o);
+          tmem_wait_ld();
+          o[0] = __float_as_uint(__uint_as_float(o[0]) * alphaA); o[1] = __float_as_uint(__uint_as_float(o[1]) * alphaA);
+          o[2] = __float_as_uint(__uint_as_float(o[2]) * alphaB); o[3] = __float_as_uint(__uint_as_float(o[3]) * alphaB);
+          o[4] = __float_as_uint(__uint_as_float(o[4]) * alphaA); o[5] = __float_as_uint(__uint_as_float(o[5]) * alphaA);
+          o[6] = __float_as_uint(__uint_as_float(o[6]) * alphaB); o[7] = __float_as_uint(__uint_as_float(o[7]) * alphaB);
+          tmem_st_16x256b_x2(lane_base + COL_O + c, o);
+        }
+        tmem_wait_st();
+      };
       if (exact) {
         float mA0 = -INFINITY, mA1 = -INFINITY, mB0 = -INFINITY, mB1 = -INFINITY;   // two chains per row
 #pragma unroll
@@ -409,8 +438,10 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (threadIdx.x == 0) DF_TR(2, g);
         // lazy rescale: keep the old reference while the max moved by < 2^8
         const float dA = fmaf(mA, scale_log2, nA), dB = fmaf(mB, scale_log2, nB);      // log2 of the largest P of the tile
-        if (dA > 8.f) { alphaA = ex2(-dA); nA = -mA * scale_log2; lA *= alphaA; moved = true; }
-        if (dB > 8.f) { alphaB = ex2(-dB); nB = -mB * scale_log2; lB *= alphaB; moved = true; }
+        float alphaA = 1.f, alphaB = 1.f;
+        if (dA > 8.f) { alphaA = ex2(-dA); nA = -mA * scale_log2; lA *= alphaA; }
+        if (dB > 8.f) { alphaB = ex2(-dB); nB = -mB * scale_log2; lB *= alphaB; }
+        if (__any_sync(0xffffffffu, dA > 8.f || dB > 8.f)) rescale_o(alphaA, alphaB);
       }
       const uint64_t scale2 = pack2(scale_log2, scale_log2), nA2 = pack2(nA, nA), nB2 = pack2(nB, nB);
       uint64_t sA = pack2(0.f, 0.f), sB = pack2(0.f, 0.f);
@@ -443,8 +474,8 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const bool over = !(tA <= 8192.f) || !(tB <= 8192.f) || tmax > 12582912.f + 13.f;   // also true for NaN sums
         if (__any_sync(0xffffffffu, over)) {           // rare: the inherited reference was too small for this tile
           const bool lost = !(tA < 3.0e38f) || !(tB < 3.0e38f) || tmax > 12582912.f + 126.f;
-          if (__any_sync(0xffffffffu, lost)) {
-            poisoned = true;                           // fp32 overflow: only S could tell the values apart, and S is gone
+          if (__any_sync(0xffffffffu, lost)) {           // fp32 overflow: only S could tell the values apart, and S is gone
+            if (lane == 0) *(volatile int*)&sm.poison[ui & 3u] = 1;
           } else {
             float pA = 0.f, pB = 0.f;
 #pragma unroll
@@ -456,8 +487,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             pA = fmaxf(pA, __shfl_xor_sync(0xffffffffu, pA, 2)); pB = fmaxf(pB, __shfl_xor_sync(0xffffffffu, pB, 2));
             // shift the reference by the exponent of the row maximum (rows that stayed below 2 keep theirs): exact powers of two
             const int kA = max(0, (int)((__float_as_uint(pA) >> 23) & 0xffu) - 127), kB = max(0, (int)((__float_as_uint(pB) >> 23) & 0xffu) - 127);
-            alphaA = __uint_as_float((uint32_t)(127 - kA) << 23);
-            alphaB = __uint_as_float((uint32_t)(127 - kB) << 23);
+            const float alphaA = __uint_as_float((uint32_t)(127 - kA) << 23), alphaB = __uint_as_float((uint32_t)(127 - kB) << 23);
             nA -= (float)kA; nB -= (float)kB;
             lA *= alphaA; lB *= alphaB; tA *= alphaA; tB *= alphaB;
 #pragma unroll
@@ -467,7 +497,7 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
               sr[4 * i + 2] = __float_as_uint(__uint_as_float(sr[4 * i + 2]) * alphaB);
               sr[4 * i + 3] = __float_as_uint(__uint_as_float(sr[4 * i + 3]) * alphaB);
             }
-            moved = true;
+            rescale_o(alphaA, alphaB);
           }
         }
       }
@@ -488,22 +518,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(DF_BAR(pv_done), (g - 1) & 1u);  // P buffer free, O quiescent
           tc_fence_after();
           if (threadIdx.x == 0) DF_TR(4, g);
-          if (__any_sync(0xffffffffu, moved)) {              // rare: rescale this warp's 16 rows of O
-#pragma unroll
-            for (int blk = 0; blk < NBLK; ++blk) {
-              uint32_t o[32];
-              tmem_ld_16x256b_x8(lane_base + COL_O + blk * HB, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i2 = 0; i2 < 8; ++i2) {
-                o[4 * i2] = __float_as_uint(__uint_as_float(o[4 * i2]) * alphaA);
-                o[4 * i2 + 1] = __float_as_uint(__uint_as_float(o[4 * i2 + 1]) * alphaA);
-                o[4 * i2 + 2] = __float_as_uint(__uint_as_float(o[4 * i2 + 2]) * alphaB);
-                o[4 * i2 + 3] = __float_as_uint(__uint_as_float(o[4 * i2 + 3]) * alphaB);
-              }
-              tmem_st_16x256b_x8(lane_base + COL_O + blk * HB, o);
-            }
-          }
         }
         tmem_st_16x128b_x8(lane_base + COL_P + hf * 32, pr);
       }
@@ -521,7 +535,6 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       sm.red_sum[ui & 1][lane16 + r8] = lA; sm.red_sum[ui & 1][lane16 + r8 + 8] = lB;
       sm.red_ref[ui & 1][lane16 + r8] = -nA; sm.red_ref[ui & 1][lane16 + r8 + 8] = -nB;
     }
-    if (SPECULATE && poisoned && lane == 0) sm.poison[ui & 3u] = 1;
     asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool item_bad = SPECULATE && *(volatile int*)&sm.poison[ui & 3u] != 0;
     if (threadIdx.x == 0) {                           // verdict for the scheduler: replay request, then the done counter

@@ -91,7 +91,7 @@ class _DistriPipelineBase:
             # stream's 0): when a K/V projection finishes, the attention grid that follows it takes the SM slots before the
             # publication kernel of the same K/V does -- a publication CTA that got there first keeps a persistent attention
             # CTA out of its SM for the whole transfer (profiles/r2_exposed_comm_n8.txt)
-            prio = int(os.environ.get("DF_COMPUTE_PRIO", "-1"))
+            prio = int(os.environ.get("DF_COMPUTE_PRIO", "-1" if cfg.n_device_per_batch > 1 else "0"))   # no publications without patch peers
             capture_stream = torch.cuda.Stream(device=cfg.device, priority=prio)
             for counter in counters:
                 graph = torch.cuda.CUDAGraph()

@@ -191,17 +191,49 @@ class ResnetBlock2D(nn.Module):
         self.output_scale_factor = 1.0
         self.fused_norm_act = False      # DistriUNetPP turns this on: SiLU runs inside the GroupNorm kernel
         self.temb_proj = None            # [b, cout] view set by the UNet per call: time_emb_proj(silu(temb)) of ALL blocks in one GEMM
+        self.temb_has_conv1_bias = False # ... which then already contains conv1.bias (conv1 runs without its bias pass)
+
+    def folds_conv1_bias(self) -> bool:
+        from .. import ops
+        return self.fused_norm_act and ops.fused_conv_bias() and _conv_of(self.conv1).bias is not None
+
+    def _tail_bias(self):
+        """conv2.bias + conv_shortcut.bias as one vector (cached on the parameters' versions): added together with the
+        residual in ONE pass after conv2 (ops.conv2d_bias_residual)."""
+        c2 = _conv_of(self.conv2)
+        if self.conv_shortcut is None or self.conv_shortcut.bias is None:
+            return c2.bias
+        key = (c2.bias._version, self.conv_shortcut.bias._version, c2.bias.data_ptr())
+        cache = getattr(self, "_tail_bias_cache", None)
+        if cache is None or cache[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("conv biases changed since the last eager call; run one eager UNet call before capture")
+            with torch.no_grad():
+                self._tail_bias_cache = cache = (key, (c2.bias.detach() + self.conv_shortcut.bias.detach()).contiguous())
+        return cache[1]
 
     def forward(self, x, temb):
         fused_halo = self.fused_norm_act and hasattr(self.conv1, "halo_plan")    # DistriGroupNorm -> DistriConv2dPP pairs
+        fold1 = self.temb_proj is not None and self.temb_has_conv1_bias          # conv1.bias is inside temb_proj
+        fused_tail = self.fused_norm_act and hasattr(self.conv2, "halo_plan") and x.is_cuda and x.dtype == torch.float16
+        k1 = dict(fold_bias=True) if fold1 else {}
         if fused_halo and self.conv1.halo_plan(x) is not None:
-            h = self.conv1.forward_padded(self.norm1(x, pad_for=self.conv1))     # norm + SiLU + halo rows in ONE kernel
+            h = self.conv1.forward_padded(self.norm1(x, pad_for=self.conv1), **k1)     # norm + SiLU + halo rows in ONE kernel
         else:
             h = self.norm1(x)
             if not self.fused_norm_act:
                 h = self.nonlinearity(h)
-            h = self.conv1(h)
+            h = self.conv1(h, **k1)
         t = self.temb_proj if self.temb_proj is not None else self.time_emb_proj(self.nonlinearity(temb))
+        if fused_tail:
+            # shortcut without its bias pass; conv2 without bias; then conv2.bias + shortcut.bias + residual in one pass
+            from .. import ops
+            sc = self.conv_shortcut
+            res = x if sc is None else F.conv2d(x, sc.weight, None if ops.fused_conv_bias() else sc.bias)
+            tail_bias = self._tail_bias() if ops.fused_conv_bias() else None
+            if fused_halo and self.conv2.halo_plan(h) is not None:
+                return self.conv2.forward_padded(self.norm2(h, addend=t, pad_for=self.conv2), residual=res, bias=tail_bias)
+            return self.conv2(self.norm2(h, addend=t), residual=res, bias=tail_bias)
         if fused_halo and self.conv2.halo_plan(h) is not None:
             h = self.conv2.forward_padded(self.norm2(h, addend=t, pad_for=self.conv2))
         else:
@@ -213,6 +245,11 @@ class ResnetBlock2D(nn.Module):
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
+
+
+def _conv_of(m):
+    """the nn.Conv2d behind a DistriConv2dPP wrapper (or the module itself)."""
+    return m.module if hasattr(m, "module") and isinstance(getattr(m, "module"), nn.Conv2d) else m
 
 
 class Downsample2D(nn.Module):
@@ -363,22 +400,28 @@ class UNet2DConditionModel(nn.Module):
         if not (emb.is_cuda and emb.dtype == torch.float16) or not blocks:
             for blk in blocks:
                 blk.temb_proj = None
+                blk.temb_has_conv1_bias = False
             return
-        key = tuple((blk.time_emb_proj.weight._version, blk.time_emb_proj.weight.data_ptr(), blk.time_emb_proj.bias._version)
-                    for blk in blocks)
+        fold = [blk.folds_conv1_bias() for blk in blocks]
+        key = tuple((blk.time_emb_proj.weight._version, blk.time_emb_proj.weight.data_ptr(), blk.time_emb_proj.bias._version,
+                     _conv_of(blk.conv1).bias._version if f else -1) for blk, f in zip(blocks, fold))
         cache = getattr(self, "_temb_cache", None)
         if cache is None or cache[0] != key:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("time-embedding weights changed since the last eager call; run one eager UNet call before capture")
             with torch.no_grad():
                 w = torch.cat([blk.time_emb_proj.weight.detach() for blk in blocks], 0).contiguous()
-                b = torch.cat([blk.time_emb_proj.bias.detach() for blk in blocks], 0).contiguous()
+                # conv1.bias rides on the embedding: GroupNorm(conv1(x) + b1 + t) == GroupNorm(conv1(x) + (t + b1)), so conv1
+                # runs without its bias pass (ResnetBlock2D.forward, fused path)
+                b = torch.cat([blk.time_emb_proj.bias.detach() + (_conv_of(blk.conv1).bias.detach() if f else 0)
+                               for blk, f in zip(blocks, fold)], 0).contiguous()
             self._temb_cache = cache = (key, w, b)
         allp = F.linear(F.silu(emb), cache[1], cache[2])
         o = 0
-        for blk in blocks:
+        for blk, f in zip(blocks, fold):
             n = blk.time_emb_proj.out_features
             blk.temb_proj = allp[:, o:o + n]
+            blk.temb_has_conv1_bias = f
             o += n
 
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, timestep_cond=None, attention_mask=None,

@@ -33,7 +33,7 @@ constexpr int NSOFTMAX_WARPS = 8;
 #ifndef DF_FMHA_SETMAXNREG
 #define DF_FMHA_SETMAXNREG 1
 #endif
-constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + (DF_FMHA_SETMAXNREG == 1 ? 4 : 2));   // 3 warpgroups: 2 x softmax, 1 x (TMA warp, MMA warp, two idle warps) -- whole
+constexpr int NTHREADS = 32 * (NSOFTMAX_WARPS + (DF_FMHA_SETMAXNREG ? 4 : 2));   // 3 warpgroups: 2 x softmax, 1 x (TMA warp, MMA warp, two idle warps) -- whole
                                                       // warpgroups so that setmaxnreg may move registers between them
 constexpr int WARP_TMA = NSOFTMAX_WARPS, WARP_MMA = NSOFTMAX_WARPS + 1;
 constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;   // S fp32 [0,128), P packed fp16 [128,192), O fp32 [192, 192 + 64*NBLK)
@@ -68,7 +68,7 @@ template <> struct Cfg<1> { static constexpr int KST = 3, VST = 2, CTAS = 2; sta
 // Two CTAs of 384 threads per SM start at 80 registers per thread (65536 / 768).  The producer warpgroup gives registers back
 // (setmaxnreg.dec 32) and the two softmax warpgroups take them (setmaxnreg.inc 104: 256 x 104 + 128 x 32 = 384 x 80): the softmax
 // loop holds a 64-value S fragment per thread and ran with spills at the 96 registers an even split allows.
-constexpr int REGS_PRODUCER = 32, REGS_SOFTMAX = DF_FMHA_SETMAXNREG == 2 ? 112 : 104;   // (2: experiment, 10 warps = a partial third warpgroup)
+constexpr int REGS_PRODUCER = 32, REGS_SOFTMAX = 104;   // (10 warps with 112 / 32 -- a partial third warpgroup -- fails at launch: profiles/r2_attn_sweep_setmaxnreg_variants.txt)
 template <> struct Cfg<2> { static constexpr int KST = 2, VST = 2, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 template <> struct Cfg<3> { static constexpr int KST = 2, VST = 1, CTAS = 1; static constexpr uint32_t TMEM = 512; };
 
@@ -94,7 +94,7 @@ struct SegInfo {
 #define DF_OPAQUE_BASES 1
 #endif
 #ifndef DF_EMU_GROUPS
-#define DF_EMU_GROUPS 4      // of the 16 column groups of a tile row, this many (evenly spread) take the polynomial exp2 (FMA/ALU
+#define DF_EMU_GROUPS 3      // of the 16 column groups of a tile row, this many (evenly spread) take the polynomial exp2 (FMA/ALU
 #endif                       // pipes) instead of MUFU
 
 #ifdef DF_TRACE

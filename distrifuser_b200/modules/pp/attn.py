@@ -19,7 +19,7 @@ _WORKSPACES: dict = {}      # device -> list of zero-initialised scratch tensors
 
 
 def _shared_workspace(device, nbytes: int) -> torch.Tensor:
-    """Scratch of the balanced-tail attention schedule (fp32 partials + self-resetting arrival tickets, df_attn_workspace_bytes).
+    """Scratch of the attention schedule (work-unit ticket counter, fp32 partials + arrival tickets of split units: df_attn_workspace_bytes).
     One buffer per device serves every attention layer: the launches are ordered on one stream.  It must start zeroed."""
     lst = _WORKSPACES.setdefault(device, [])
     if not lst or lst[-1].numel() < nbytes:

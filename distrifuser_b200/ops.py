@@ -1,4 +1,6 @@
 """Small fused ops on the per-step path that are not reference wrappers (thin shims over the C ABI)."""
+import os as _os
+
 import torch
 
 from . import _lib
@@ -31,6 +33,41 @@ def add_layernorm(x: torch.Tensor, r: torch.Tensor | None, norm: torch.nn.LayerN
                                            norm.bias.data_ptr(), x.numel() // C, C, float(norm.eps),
                                            torch.cuda.current_stream().cuda_stream), "df_add_layernorm")
     return s, y
+
+
+def fused_conv_bias() -> bool:
+    """DF_CONV_BIAS=torch restores F.conv2d's own bias handling (cudnn_convolution + broadcast add_)."""
+    return _os.environ.get("DF_CONV_BIAS", "fused") != "torch"
+
+
+def conv2d_bias_residual(x: torch.Tensor, conv: torch.nn.Conv2d, padding, residual: torch.Tensor | None = None,
+                         bias: torch.Tensor | None = None, fold_bias: bool = False) -> torch.Tensor:
+    """conv(x) + bias (+ residual): the convolution runs in cuDNN WITHOUT bias and one vectorised pass adds `bias` (default
+    conv.bias) and the residual (df_bias_residual_add).  fold_bias: the caller adds the bias elsewhere (e.g. into the addend of
+    the following GroupNorm) -- no pass at all.  Falls back to F.conv2d for anything but fp16 CUDA NHWC tensors."""
+    import torch.nn.functional as F
+    b = conv.bias if bias is None else bias
+    ok = (x.is_cuda and x.dtype == torch.float16 and fused_conv_bias() and conv.out_channels % 8 == 0 and
+          x.is_contiguous(memory_format=torch.channels_last))
+    if not ok:
+        out = F.conv2d(x, conv.weight, None if fold_bias else b, stride=conv.stride, padding=padding)
+        return out if residual is None else residual + out
+    out = F.conv2d(x, conv.weight, None, stride=conv.stride, padding=padding)
+    if (b is None or fold_bias) and residual is None:
+        return out
+    if not out.is_contiguous(memory_format=torch.channels_last):
+        out = out.contiguous(memory_format=torch.channels_last)
+    if b is None or fold_bias:
+        return residual + out
+    if residual is not None:
+        assert residual.shape == out.shape and residual.dtype == out.dtype
+        if not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+    n, c, h, w = out.shape
+    _lib.check(_lib.lib().df_bias_residual_add(out.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                               b.data_ptr(), out.data_ptr(), n * h * w, c,
+                                               torch.cuda.current_stream().cuda_stream), "df_bias_residual_add")
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------- tcgen05 GEMM (csrc/linear.cu)

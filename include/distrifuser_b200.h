@@ -137,9 +137,11 @@ int df_halo_assemble(df_comm_t comm, const void* x, void* xp, int b, int h, int 
  *      softmax scale is 1/sqrt(d) unless scale > 0. ------------------------------------------------- */
 int df_attn_make_kvmaps(df_comm_t comm, uint64_t tensor_off, uint64_t slot_bytes, int b, int lseg, int heads,
                         int d, void* maps_out /* device, DF_NBANKS*world*DF_TENSORMAP_BYTES */, void* stream);
-/* Small grids (short per-rank Q at n >= 2) split the K/V range of a q-tile over several CTAs and combine the partial
- * (O, max, sum) triples in a second kernel; that needs df_attn_workspace_bytes() of scratch (0 = single pass).  Passing a
- * null / too small workspace simply disables the split. */
+/* Scratch of a launch: df_attn_workspace_bytes() bytes, ZERO-INITIALISED ONCE by the caller and then reusable by any number of
+ * stream-ordered launches (every counter in it resets itself).  It holds the ticket counter from which the persistent CTAs
+ * of a grid that fills the SMs draw their work units and, for small grids (short per-rank Q at n >= 2), the fp32 partials and
+ * arrival tickets of units whose K/V range is cut over several CTAs (merged in-kernel by the last part to arrive).  Passing a
+ * null / too small workspace is legal: every CTA then walks a static list of whole units. */
 size_t df_attn_workspace_bytes(int b, int lq, int lseg, int nseg, int heads, int d);
 int df_attn_fwd(df_comm_t comm, const void* q, const void* kv_own, void* out, const void* kvmaps,
                 int b, int lq, int lseg, int heads, int d, int64_t q_pitch, int64_t kv_pitch, int64_t o_pitch,
@@ -158,6 +160,12 @@ int df_output_gather(df_comm_t comm, const void* strip, void* out, int B, int C,
  *      Not one of the reference's wrapped modules (diffusers FeedForward) but on the per-step
  *      path inside DistriUNetPP.forward; in:[rows, 2*cols] fp16 (pitch in_pitch elements), out:[rows, cols]. ---- */
 int df_geglu(const void* in, void* out, int64_t rows, int cols, int64_t in_pitch, int64_t out_pitch, void* stream);
+
+/* ---- out = a + bias[c] (+ residual) on NHWC fp16 activations [rows = b*h*w, C], in one pass (out may alias a).
+ *      Replaces the broadcast bias `add_` that torch runs after every cudnn_convolution (F.conv2d, used by
+ *      distrifuser/modules/pp/conv2d.py:41,110) and the residual add of diffusers' ResnetBlock2D.forward. -------------- */
+int df_bias_residual_add(const void* a, const void* residual /* nullable */, const void* bias, void* out, int64_t rows, int C,
+                         void* stream);
 
 /* ---- fused residual add + LayerNorm of BasicTransformerBlock: s = x + r (fp16, written to s_out when non-null; r may
  *      be null = plain LayerNorm), y = LayerNorm(s) * gamma + beta.  x, r, s_out, y: [rows, C] contiguous fp16. ---- */

@@ -495,3 +495,34 @@ def test_publish_strided_rows():
     ok = torch.equal(got, kv)
     arena.close()
     assert ok
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+@pytest.mark.parametrize("shape", [(2, 320, 16, 24), (1, 1280, 5, 7), (3, 8, 33, 9)])
+def test_bias_residual_add(shape, with_res):
+    """out = a + bias[c] (+ residual) on NHWC fp16, in place on a: one fp16 rounding of the fp32 sum."""
+    from distrifuser_b200 import _lib
+    torch.manual_seed(7)
+    n, c, h, w = shape
+    a = torch.randn(n, c, h, w, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    r = torch.randn_like(a) if with_res else None
+    bias = torch.randn(c, device="cuda", dtype=torch.float16)
+    ref = a.float() + bias.float()[None, :, None, None] + (r.float() if with_res else 0)
+    _lib.check(_lib.lib().df_bias_residual_add(a.data_ptr(), r.data_ptr() if with_res else None, bias.data_ptr(), a.data_ptr(),
+                                               n * h * w, c, torch.cuda.current_stream().cuda_stream), "df_bias_residual_add")
+    torch.cuda.synchronize()
+    assert torch.equal(a, ref.half())
+
+
+def test_conv2d_bias_residual_matches_torch():
+    """ops.conv2d_bias_residual (cuDNN without bias + one bias / residual pass) against F.conv2d + add."""
+    from distrifuser_b200 import ops
+    torch.manual_seed(8)
+    conv = torch.nn.Conv2d(64, 128, 3, padding=1).cuda().half().to(memory_format=torch.channels_last)
+    x = torch.randn(2, 64, 20, 28, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(2, 128, 20, 28, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        ref = torch.nn.functional.conv2d(x.float(), conv.weight.float(), conv.bias.float(), padding=1) + res.float()
+        out = ops.conv2d_bias_residual(x, conv, conv.padding, residual=res)
+        out2 = ops.conv2d_bias_residual(x, conv, conv.padding, fold_bias=True) + conv.bias[None, :, None, None] + res
+    assert (out.float() - ref).abs().max().item() < 3e-2 and (out2.float() - ref).abs().max().item() < 3e-2

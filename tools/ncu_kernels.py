@@ -14,7 +14,7 @@ from distrifuser_b200 import _lib, ops  # noqa: E402
 L = _lib.lib()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-which = set((sys.argv[1] if len(sys.argv) > 1 else "attn,gn,geglu,ln,publish,linear").split(","))
+which = set((sys.argv[1] if len(sys.argv) > 1 else "attn,gn,geglu,ln,bias,publish,linear").split(","))
 
 
 def profiled(fn):
@@ -63,6 +63,12 @@ if "ln" in which:
         r = torch.randn(rows, Cc, device="cuda", dtype=torch.float16)
         ln = torch.nn.LayerNorm(Cc).cuda().half()
         profiled(lambda: ops.add_layernorm(x, r, ln))
+if "bias" in which:
+    for (Cc, hh, ww) in [(320, 128, 128), (1280, 32, 32)]:
+        a_ = torch.randn(2, Cc, hh, ww, device="cuda", dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+        r_ = torch.randn_like(a_)
+        bv = torch.randn(Cc, device="cuda", dtype=torch.float16)
+        profiled(lambda: _lib.check(L.df_bias_residual_add(a_.data_ptr(), r_.data_ptr(), bv.data_ptr(), a_.data_ptr(), 2 * hh * ww, Cc, st), "bias"))
 if "publish" in which:
     from helpers import LoopbackArena
     n, nbytes = 2, 1 * 2048 * 2 * 1280 * 2                 # K|V of level 1 at n=2: [1, 2048, 2*640] ... 10 MB

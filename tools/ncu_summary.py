@@ -19,6 +19,7 @@ LABELS = [  # (kernel substring, label, traffic key or None) in launch order of 
     ("gn_fused", "GroupNorm fused (stats+apply+SiLU)  b2 C1280 32x32", None),
     ("geglu", "GEGLU gate  rows 8192 cols 2560", None), ("geglu", "GEGLU gate  rows 2048 cols 5120", None),
     ("add_layernorm", "add+LayerNorm  rows 8192 C640", None), ("add_layernorm", "add+LayerNorm  rows 2048 C1280", None),
+    ("bias_residual", "conv bias + residual  b2 C320 128x128", None), ("bias_residual", "conv bias + residual  b2 C1280 32x32", None),
     ("publish", "K|V publication 10.5 MB to one peer (loopback)", None),
     ("linear_kernel", "GEMM + GEGLU  M2048 K1280 D5120 (level-2 FF1)", None),
     ("linear_kernel", "GEMM bias+residual  M2048 N1280 K5120 (level-2 FF2)", None),

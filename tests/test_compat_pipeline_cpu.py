@@ -113,3 +113,35 @@ def test_batched_time_embedding_is_noop_on_cpu():
     assert len(unet._resnets()) == 2 * 2 + 2 + 2 * 3            # down (2 x 2) + mid (2) + up (2 x 3)
     unet._batched_temb(torch.randn(1, 128))                     # fp32 CPU embedding: nothing is batched
     assert all(blk.temb_proj is None for blk in unet._resnets())
+
+
+def test_conv2d_bias_residual_cpu_fallback_matches_conv2d():
+    """ops.conv2d_bias_residual on CPU / fp32 is plain F.conv2d (+ residual); fold_bias drops the bias."""
+    import torch
+    from distrifuser_b200 import ops
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(8, 16, 3, padding=1)
+    x, res = torch.randn(2, 8, 6, 5), torch.randn(2, 16, 6, 5)
+    with torch.no_grad():
+        ref = conv(x)
+        assert torch.allclose(ops.conv2d_bias_residual(x, conv, conv.padding), ref)
+        assert torch.allclose(ops.conv2d_bias_residual(x, conv, conv.padding, residual=res), ref + res)
+        assert torch.allclose(ops.conv2d_bias_residual(x, conv, conv.padding, fold_bias=True), ref - conv.bias[None, :, None, None], atol=1e-6)
+        other = torch.randn(16)
+        assert torch.allclose(ops.conv2d_bias_residual(x, conv, conv.padding, bias=other), ref - conv.bias[None, :, None, None] + other[None, :, None, None], atol=1e-6)
+
+
+def test_resnet_block_does_not_fold_biases_on_cpu():
+    """The fused bias paths of compat.ResnetBlock2D are CUDA/fp16 only: on CPU the block is the textbook sequence."""
+    import torch
+    from distrifuser_b200.compat.unet_2d_condition import ResnetBlock2D
+    torch.manual_seed(0)
+    blk = ResnetBlock2D(32, 64, 16, 8, 1e-5)
+    x, temb = torch.randn(1, 32, 6, 6), torch.randn(1, 16)
+    assert not blk.folds_conv1_bias()
+    with torch.no_grad():
+        h = blk.conv1(torch.nn.functional.silu(blk.norm1(x)))
+        h = h + blk.time_emb_proj(torch.nn.functional.silu(temb))[:, :, None, None]
+        h = blk.conv2(torch.nn.functional.silu(blk.norm2(h)))
+        ref = blk.conv_shortcut(x) + h
+        assert torch.allclose(blk(x, temb), ref, atol=1e-5)

@@ -1,5 +1,5 @@
 """Counts the Blackwell-native SASS mnemonics per kernel of libdistrifuser_b200.so (cuobjdump -sass): UTC*MMA (tcgen05.mma),
-LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA), UTCBAR (tcgen05.commit), SYNCS (mbarrier), plus legacy HMMA (must be 0).
+LDTM / STTM (tcgen05.ld / st), UTMALDG / UTMASTG (TMA), UTCBAR (tcgen05.commit), SYNCS (mbarrier), USETMAXREG (setmaxnreg), LDL / STL (spills), plus legacy HMMA (must be 0).
     python tools/sass_summary.py > profiles/r2_sass_mnemonics.txt"""
 import collections
 import os
@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "distrifuser_b200", "libdistrifuser_b200.so")
 sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 WATCH = ("UTCHMMA", "UTCQMMA", "UTCIMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCBAR", "SYNCS", "HMMA", "HGMMA", "MUFU", "FFMA2", "FADD2",
-         "UCGABAR", "ACQBULK", "RED", "ATOM")
+         "UCGABAR", "ACQBULK", "RED", "ATOM", "USETMAXREG", "FMNMX3", "LDL", "STL")
 cur, per = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)

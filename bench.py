@@ -32,7 +32,11 @@ for p in (ROOT,):
 
 STEPS_PER_IMAGE = 50
 print_json = print
-METRIC = "SDXL 50-step latency (ms/image)"
+METRIC = "SDXL 50-step latency (ms/image)"          # BASELINE.json's metric; --model sd15 (configs[4]) reports the same quantity for SD1.5
+
+
+def metric_name(model: str) -> str:
+    return METRIC if model == "sdxl" else METRIC.replace("SDXL", "SD1.5")
 
 
 def parse():
@@ -212,7 +216,7 @@ def run_reference(a):
         return
     r = cpu_reference_samples(a.model, a.resolution, max(1, a.steps), max(1, a.warmup), a.cpu_budget_s)
     ms_image = r["ms_image"]
-    line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": a.gpus, "steps": r["timed"], "warmup": r["warm"],
+    line = {"metric": metric_name(a.model), "value": ms_image, "unit": "ms/image", "n_gpus": a.gpus, "steps": r["timed"], "warmup": r["warm"],
             "steps_requested": a.steps, "warmup_requested": a.warmup,
             "ms_per_step": r["sample_s"] * 1e3, "ms_per_step_is": "one bounded sample (see cpu_baseline.sample), not one image",
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
@@ -285,7 +289,7 @@ def run_reference_gpu(a):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_image = ms.item() / a.steps
     if cfg.rank == 0:
-        line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": max(1, a.warmup),
+        line = {"metric": metric_name(a.model), "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": max(1, a.warmup),
                 "ms_per_step": ms_image, "ms_per_denoise_step": ms_image / STEPS_PER_IMAGE, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic", "impl": "reference-gpu",
                 "config": {"workload": f"SDXL UNet {R}x{R}, 50-step Euler, CFG batch 2, random-init weights; UNMODIFIED reference "
@@ -661,7 +665,7 @@ def run_ours(a):
     if rank == 0:
         n, b = cfg.n_device_per_batch, (1 if (cfg.do_classifier_free_guidance and cfg.split_batch and world > 1) else 2)
         h2d = io["embeds_h"].numel() * 2 + (io["pooled_h"].numel() * 2 if io["pooled_h"] is not None else 0) + io["lat_h"].numel() * 4
-        line = {"metric": METRIC, "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": warm,
+        line = {"metric": metric_name(a.model), "value": ms_image, "unit": "ms/image", "n_gpus": world, "steps": a.steps, "warmup": warm,
                 "ms_per_step": ms_image, "ms_per_denoise_step": ms_image / STEPS_PER_IMAGE, "higher_is_better": False,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
                 "config": {"workload": f"{a.model.upper()} UNet {R}x{R}, 50-step Euler, CFG batch 2, random-init weights",

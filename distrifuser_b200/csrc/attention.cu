@@ -7,16 +7,20 @@
 //     F.scaled_dot_product_attention -> S = Q K^T and O += P V as tcgen05.mma tiles, accumulators in TMEM
 // and the SDPA of DistriCrossAttentionPP.forward (attn.py:79-87) with nseg = 1, lseg = 77.
 //
-// Persistent CTAs (320 threads, TWO per SM at d <= 64: 256 TMEM columns, ~97 KB smem each) walk work units = one 128-row Q
-// tile of one (batch, head):
+// Persistent CTAs (384 threads = 3 warpgroups, TWO per SM at d <= 64: 256 TMEM columns, ~97 KB smem each; setmaxnreg moves
+// registers from the producer warpgroup to the two softmax warpgroups) walk work units = one 128-row Q tile of one (batch, head):
 //   warps 0-7  softmax: warp w owns 16 rows and all 128 S columns of them in the 16x256b TMEM fragment layout (a row lives in
-//              one quad).  tcgen05.ld S -> exp2 in place (packed FFMA2/FADD2, a quarter of the lanes on a polynomial instead
-//              of MUFU) against a SPECULATIVE exponent reference -- row maxima are only computed for the first tile of a unit
-//              and for the rare tile whose row sums show the reference was too small -- then P -> fp16 -> TMEM, lazy O
-//              correction, epilogue O / l -> HBM (or fp32 partials merged by the last part of a split unit)
-//   warp 8     TMA producer: Q per unit, then K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
+//              one quad).  tcgen05.ld S (S is released at once) -> exp2 in place (packed FFMA2/FADD2, 3 of 16 column groups on a
+//              polynomial instead of MUFU) against a SPECULATIVE exponent reference -- row maxima are only computed for the
+//              first tile of an item; a later tile whose row sums show the reference was too small is repaired in registers
+//              (power-of-two rescale of P, l, O), and an item whose exponentials overflowed fp32 is re-run exactly -- then
+//              P -> fp16 -> TMEM, epilogue O / l -> HBM (or fp32 partials merged by the last part of a split unit)
+//   warp 8     scheduler + TMA producer: hands out work items through a two-entry ring (whole units drawn from an atomic ticket
+//              counter when the grid fills the SMs, a static one-item list otherwise, replays first), then Q per item and
+//              K (3 stages) / V (2 stages) tiles through mbarrier rings; waits the peers' flags
 //   warp 9     MMA issuer (one lane): S = Q K_j^T (SS), O += P V_j (A = P from TMEM, B = V MN-major); Q K_{j+1}^T is
 //              issued once the softmax warps have released S_j (s_free)
+//   warps 10-11 idle (they complete the third warpgroup: setmaxnreg works on whole warpgroups)
 // TMEM columns: S [0,128) P [128,192) O [192, 192 + 64*NBLK)   (fp32 S/O, packed fp16 P)
 
 #include "tc_ptx.cuh"

@@ -60,7 +60,7 @@ struct __align__(1024) SmemT {
   uint64_t o_free;            // the epilogue of the previous work unit has pulled O out of TMEM
   uint64_t sched_full[2];     // work-item ring: the TMA lane (scheduler) publishes the next item code, the other roles consume it
   int sched_code[2];
-  int replay_code[8];         // items whose speculative pass overflowed fp32 (softmax thread 0 -> scheduler), re-run exactly
+  uint32_t replay_code[8];    // items whose speculative pass overflowed fp32 (softmax thread 0 -> scheduler), re-run exactly
   uint32_t replay_wr;
   uint32_t items_done;        // items whose verdict (clean / replay) has been published by the softmax warps
   int poison[4];              // [item & 3]: set by any softmax warp that had to give up on the item
@@ -89,6 +89,12 @@ __device__ __forceinline__ float2 ld_f2(const float2* p) {          // coherent 
   asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
   return r;
 }
+
+// Scheduler <-> softmax signalling words in shared memory (replay ring, verdict counter) are accessed with shared-memory
+// atomics only: one writer, one polling reader, ordered by __threadfence_block -- no barrier involved, so plain or volatile
+// accesses would be (benign) races in the eyes of the memory model and of compute-sanitizer's racecheck.
+__device__ __forceinline__ uint32_t sig_load(uint32_t* p) { return atomicAdd(p, 0u); }
+__device__ __forceinline__ void sig_store(uint32_t* p, uint32_t v) { atomicExch(p, v); }
 
 struct SegInfo {
   int32_t rank[DF_MAX_WORLD];  // world rank holding segment s
@@ -226,8 +232,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       for (;; ++ui) {
         int code;
         for (;;) {
-          if (replay_rd != *(volatile uint32_t*)&sm.replay_wr) {
-            code = *(volatile int*)&sm.replay_code[replay_rd & 7u] | ITEM_EXACT;
+          if (replay_rd != sig_load(&sm.replay_wr)) {
+            __threadfence_block();
+            code = (int)sig_load(&sm.replay_code[replay_rd & 7u]) | ITEM_EXACT;
             ++replay_rd;
             break;
           }
@@ -236,9 +243,9 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             fresh_left = false;                            // this CTA's one failing draw
             if (sched.dyn && next_t == n_fresh + gridDim.x - 1u) *sched_ctr = 0u;   // last draw of the launch: self-resetting
           }
-          if (*(volatile uint32_t*)&sm.items_done == ui) {   // every published item has its verdict ...
+          if (sig_load(&sm.items_done) == ui) {            // every published item has its verdict ...
             __threadfence_block();
-            if (replay_rd != *(volatile uint32_t*)&sm.replay_wr) continue;   // ... and the last one asked for a replay
+            if (replay_rd != sig_load(&sm.replay_wr)) continue;   // ... and the last one asked for a replay
             code = ITEM_END;
             break;
           }
@@ -544,13 +551,13 @@ fmha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (threadIdx.x == 0) {                           // verdict for the scheduler: replay request, then the done counter
       sm.poison[(ui + 2u) & 3u] = 0;                  // the entry two items ahead (nobody reads or sets it now)
       if (item_bad) {
-        const uint32_t wr = sm.replay_wr;
-        *(volatile int*)&sm.replay_code[wr & 7u] = code & ITEM_MASK;
+        const uint32_t wr = sig_load(&sm.replay_wr);  // this thread is the only writer
+        sig_store(&sm.replay_code[wr & 7u], (uint32_t)(code & ITEM_MASK));
         __threadfence_block();
-        *(volatile uint32_t*)&sm.replay_wr = wr + 1u;
+        sig_store(&sm.replay_wr, wr + 1u);
       }
       __threadfence_block();
-      *(volatile uint32_t*)&sm.items_done = ui + 1u;
+      sig_store(&sm.items_done, ui + 1u);
     }
     const int half = hr;
     const int row = quad * 32 + lane;

@@ -71,7 +71,6 @@ def conv2d_bias_residual(x: torch.Tensor, conv: torch.nn.Conv2d, padding, residu
 
 
 # ---------------------------------------------------------------------------------------------------- tcgen05 GEMM (csrc/linear.cu)
-import os as _os
 
 # which Linear layers run on the hand-written GEMM: comma list out of {geglu, qkv, out, ff2, proj}; "all" / "none".
 # Default = the set measured faster than cuBLAS on B200 (tools/bench_linear.py, profiles/r2_linear_vs_cublas.txt).
